@@ -1,0 +1,291 @@
+"""ctypes binding of the C-ABI in include/ellc_gn.h (libellc_gn.so).
+
+This is plumbing for tests and bench.py; the product is the CUDA library.  There is no fallback: if the shared
+library is missing the import of the symbols fails loudly, and every compute call fails with ELLC_ERR_CUDA when no
+sm_100 device is usable.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+LEVELS = 4
+MAX_TRACE_ITERS = 16
+ARITH_FAST, ARITH_STRICT = 0, 1
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libellc_gn.so")
+
+
+class EllcError(RuntimeError):
+    pass
+
+
+class Config(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+                ("max_iter", C.c_int32 * LEVELS), ("huber_d", C.c_float), ("camera_pixel_noise_2", C.c_float),
+                ("weight", C.c_float * 6), ("stop_threshold", C.c_float), ("arithmetic", C.c_int32),
+                ("jacobian_at_warped", C.c_int32), ("max_keyframes", C.c_int32), ("max_frames", C.c_int32),
+                ("ctas_per_pair", C.c_int32), ("device", C.c_int32)]
+
+
+class Pair(C.Structure):
+    _fields_ = [("kf_slot", C.c_int32), ("frame_slot", C.c_int32), ("init_pose", C.c_float * 6), ("flags", C.c_int32)]
+
+
+class Result(C.Structure):
+    _fields_ = [("pose", C.c_float * 6), ("H", C.c_float * 21), ("b", C.c_float * 6),
+                ("n_selected", C.c_int32 * LEVELS), ("n_iters", C.c_int32 * LEVELS),
+                ("res_first", C.c_float * LEVELS), ("res_last", C.c_float * LEVELS),
+                ("weighted_pose", C.c_float * LEVELS), ("n_oob", C.c_int32 * LEVELS),
+                ("status", C.c_int32), ("reserved", C.c_int32 * 6)]
+
+
+class IterTrace(C.Structure):
+    _fields_ = [("H", C.c_float * 36), ("b", C.c_float * 6), ("delta", C.c_float * 6), ("weighted_pose", C.c_float),
+                ("pose_after", C.c_float * 6), ("res_sum", C.c_float), ("weight_sum", C.c_float),
+                ("n_oob", C.c_int32), ("executed", C.c_int32), ("pad", C.c_int32 * 5)]
+
+
+assert C.sizeof(Result) == 256 and C.sizeof(IterTrace) == 256 and C.sizeof(Pair) == 36
+
+PAIR_DTYPE = np.dtype([("kf_slot", "<i4"), ("frame_slot", "<i4"), ("init_pose", "<f4", 6), ("flags", "<i4")])
+RESULT_DTYPE = np.dtype([("pose", "<f4", 6), ("H", "<f4", 21), ("b", "<f4", 6), ("n_selected", "<i4", 4),
+                         ("n_iters", "<i4", 4), ("res_first", "<f4", 4), ("res_last", "<f4", 4),
+                         ("weighted_pose", "<f4", 4), ("n_oob", "<i4", 4), ("status", "<i4"), ("reserved", "<i4", 6)])
+TRACE_DTYPE = np.dtype([("H", "<f4", 36), ("b", "<f4", 6), ("delta", "<f4", 6), ("weighted_pose", "<f4"),
+                        ("pose_after", "<f4", 6), ("res_sum", "<f4"), ("weight_sum", "<f4"), ("n_oob", "<i4"),
+                        ("executed", "<i4"), ("pad", "<i4", 5)])
+assert PAIR_DTYPE.itemsize == 36 and RESULT_DTYPE.itemsize == 256 and TRACE_DTYPE.itemsize == 256
+
+# every symbol include/ellc_gn.h declares
+SYMBOLS = ["ellc_default_config", "ellc_create", "ellc_destroy", "ellc_last_error_string", "ellc_version",
+           "ellc_upload_frame", "ellc_upload_keyframe", "ellc_frame_image_devptr", "ellc_keyframe_devptrs",
+           "ellc_prepare_frames", "ellc_prepare_keyframes", "ellc_track_batch", "ellc_track_batch_async",
+           "ellc_synchronize", "ellc_gn_evaluate", "ellc_solve_update", "ellc_read_frame_level",
+           "ellc_read_keyframe_level", "ellc_level_dims", "ellc_concat_relative", "ellc_concat_origin",
+           "ellc_se3_exp", "ellc_launch_count", "ellc_reset_launch_count", "ellc_stream", "ellc_last_track_kernel_ms"]
+
+_lib = None
+
+
+def lib():
+    """Load libellc_gn.so (built in-tree by _build.build()).  Raises if it is missing -- no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise EllcError(f"{_LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                            "(the CUDA extension is mandatory, there is no CPU fallback)")
+        L = C.CDLL(_LIB_PATH)
+        L.ellc_last_error_string.restype = C.c_char_p
+        L.ellc_last_error_string.argtypes = [C.c_void_p]
+        L.ellc_version.restype = C.c_char_p
+        L.ellc_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
+        L.ellc_destroy.argtypes = [C.c_void_p]
+        L.ellc_upload_frame.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        L.ellc_upload_keyframe.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ellc_frame_image_devptr.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]
+        L.ellc_keyframe_devptrs.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                            C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+        L.ellc_prepare_frames.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        L.ellc_prepare_keyframes.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        L.ellc_track_batch.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ellc_track_batch_async.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.ellc_synchronize.argtypes = [C.c_void_p]
+        L.ellc_gn_evaluate.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ellc_solve_update.argtypes = [C.c_void_p] + [C.c_void_p] * 5 + [C.POINTER(C.c_float)]
+        L.ellc_read_frame_level.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ellc_read_keyframe_level.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
+        L.ellc_level_dims.argtypes = [C.c_void_p, C.c_int32] + [C.POINTER(C.c_int32)] * 4
+        L.ellc_concat_relative.argtypes = [C.c_void_p] * 3
+        L.ellc_concat_origin.argtypes = [C.c_void_p] * 3
+        L.ellc_se3_exp.argtypes = [C.c_void_p] * 2
+        L.ellc_launch_count.restype = C.c_int64
+        L.ellc_launch_count.argtypes = [C.c_void_p]
+        L.ellc_reset_launch_count.argtypes = [C.c_void_p]
+        L.ellc_stream.restype = C.c_void_p
+        L.ellc_stream.argtypes = [C.c_void_p]
+        L.ellc_last_track_kernel_ms.restype = C.c_float
+        L.ellc_last_track_kernel_ms.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def default_config(width, height, **over):
+    cfg = Config()
+    lib().ellc_default_config(C.byref(cfg), int(width), int(height))
+    for k, v in over.items():
+        if k in ("max_iter", "weight"):
+            arr = getattr(cfg, k)
+            for i, x in enumerate(v):
+                arr[i] = x
+        else:
+            setattr(cfg, k, v)
+    return cfg
+
+
+def concat_relative(a, b):
+    a = np.ascontiguousarray(a, np.float32); b = np.ascontiguousarray(b, np.float32)
+    out = np.empty(6, np.float32)
+    lib().ellc_concat_relative(_p(a), _p(b), _p(out))
+    return out
+
+
+def concat_origin(a, b):
+    a = np.ascontiguousarray(a, np.float32); b = np.ascontiguousarray(b, np.float32)
+    out = np.empty(6, np.float32)
+    lib().ellc_concat_origin(_p(a), _p(b), _p(out))
+    return out
+
+
+def se3_exp(pose):
+    pose = np.ascontiguousarray(pose, np.float32)
+    out = np.empty(16, np.float32)
+    lib().ellc_se3_exp(_p(pose), _p(out))
+    return out.reshape(4, 4)
+
+
+class Tracker:
+    """Thin owner of one ellc_handle (one CUDA stream + device pools)."""
+
+    def __init__(self, cfg):
+        self.cfg = cfg
+        self._h = C.c_void_p()
+        rc = lib().ellc_create(C.byref(cfg), C.byref(self._h))
+        if rc != 0:
+            raise EllcError(f"ellc_create failed ({rc}): {lib().ellc_last_error_string(None).decode()}")
+
+    def close(self):
+        if self._h:
+            lib().ellc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise EllcError(f"ellc call failed ({rc}): {lib().ellc_last_error_string(self._h).decode()}")
+
+    # -- uploads from host memory
+    def upload_frame(self, slot, image):
+        image = np.ascontiguousarray(image, np.uint8)
+        assert image.shape == (self.cfg.height, self.cfg.width)
+        self._keep = getattr(self, "_keep", [])
+        self._keep.append(image)
+        self._chk(lib().ellc_upload_frame(self._h, slot, _p(image)))
+
+    def upload_keyframe(self, slot, image, depth, var):
+        image = np.ascontiguousarray(image, np.uint8)
+        d = [np.ascontiguousarray(a, np.float32) for a in depth]
+        v = [np.ascontiguousarray(a, np.float32) for a in var]
+        dp = (C.c_void_p * LEVELS)(*[_p(a) for a in d])
+        vp = (C.c_void_p * LEVELS)(*[_p(a) for a in v])
+        self._keep = getattr(self, "_keep", [])
+        self._keep += [image] + d + v
+        self._chk(lib().ellc_upload_keyframe(self._h, slot, _p(image), dp, vp))
+
+    def synchronize(self):
+        self._chk(lib().ellc_synchronize(self._h))
+        self._keep = []
+
+    # -- device-resident inputs
+    def frame_image_devptr(self, slot):
+        p = C.c_void_p()
+        self._chk(lib().ellc_frame_image_devptr(self._h, slot, C.byref(p)))
+        return p.value
+
+    def keyframe_devptrs(self, slot):
+        pi, pd, pv = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        off = (C.c_int64 * (LEVELS + 1))()
+        self._chk(lib().ellc_keyframe_devptrs(self._h, slot, C.byref(pi), C.byref(pd), C.byref(pv), off))
+        return pi.value, pd.value, pv.value, list(off)
+
+    def prepare_frames(self, slots):
+        s = np.ascontiguousarray(slots, np.int32)
+        self._chk(lib().ellc_prepare_frames(self._h, len(s), _p(s)))
+
+    def prepare_keyframes(self, slots):
+        s = np.ascontiguousarray(slots, np.int32)
+        self._chk(lib().ellc_prepare_keyframes(self._h, len(s), _p(s)))
+
+    # -- hot path
+    @staticmethod
+    def make_pairs(kf_slots, frame_slots, init_poses=None, flags=0):
+        n = len(kf_slots)
+        pairs = np.zeros(n, PAIR_DTYPE)
+        pairs["kf_slot"] = kf_slots
+        pairs["frame_slot"] = frame_slots
+        if init_poses is not None:
+            pairs["init_pose"] = np.asarray(init_poses, np.float32).reshape(n, 6)
+        pairs["flags"] = flags
+        return pairs
+
+    def track_batch(self, pairs, want_trace=False):
+        pairs = np.ascontiguousarray(pairs, PAIR_DTYPE)
+        n = len(pairs)
+        res = np.zeros(n, RESULT_DTYPE)
+        tr = np.zeros((n, LEVELS, MAX_TRACE_ITERS), TRACE_DTYPE) if want_trace else None
+        self._chk(lib().ellc_track_batch(self._h, n, _p(pairs), _p(res), _p(tr)))
+        self._keep = []
+        return (res, tr) if want_trace else res
+
+    def track_batch_async(self, pairs):
+        pairs = np.ascontiguousarray(pairs, PAIR_DTYPE)
+        dres = C.c_void_p()
+        self._chk(lib().ellc_track_batch_async(self._h, len(pairs), _p(pairs), C.byref(dres)))
+        return dres.value
+
+    def gn_evaluate(self, kf_slot, frame_slot, level, pose, want_weights=False):
+        pose = np.ascontiguousarray(pose, np.float32)
+        out = np.zeros(1, TRACE_DTYPE)
+        w = None
+        if want_weights:
+            cols, rows = self.level_dims(level)[2:]
+            w = np.zeros((rows, cols), np.float32)
+        self._chk(lib().ellc_gn_evaluate(self._h, kf_slot, frame_slot, level, _p(pose), _p(out), _p(w)))
+        return (out[0], w) if want_weights else out[0]
+
+    def solve_update(self, H, b, pose):
+        H = np.ascontiguousarray(np.asarray(H, np.float32).reshape(36))
+        b = np.ascontiguousarray(b, np.float32); pose = np.ascontiguousarray(pose, np.float32)
+        po = np.empty(6, np.float32); de = np.empty(6, np.float32); wp = C.c_float()
+        self._chk(lib().ellc_solve_update(self._h, _p(H), _p(b), _p(pose), _p(po), _p(de), C.byref(wp)))
+        return po, de, wp.value
+
+    # -- read-back
+    def level_dims(self, level):
+        a, b, c, d = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        self._chk(lib().ellc_level_dims(self._h, level, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return a.value, b.value, c.value, d.value
+
+    def read_frame_level(self, slot, level):
+        pw, ph, cols, rows = self.level_dims(level)
+        img = np.empty((ph, pw), np.uint8); gx = np.empty((rows, cols), np.float32); gy = np.empty((rows, cols), np.float32)
+        self._chk(lib().ellc_read_frame_level(self._h, slot, level, _p(img), _p(gx), _p(gy)))
+        return img, gx, gy
+
+    def read_keyframe_level(self, slot, level):
+        pw, ph, cols, rows = self.level_dims(level)
+        img = np.empty((ph, pw), np.uint8); mask = np.empty((rows, cols), np.uint8); cnt = C.c_int32()
+        self._chk(lib().ellc_read_keyframe_level(self._h, slot, level, _p(img), _p(mask), C.byref(cnt)))
+        return img, mask, cnt.value
+
+    # -- introspection
+    def launch_count(self):
+        return lib().ellc_launch_count(self._h)
+
+    def reset_launch_count(self):
+        lib().ellc_reset_launch_count(self._h)
+
+    def stream(self):
+        return lib().ellc_stream(self._h)
+
+    def last_track_kernel_ms(self):
+        return lib().ellc_last_track_kernel_ms(self._h)

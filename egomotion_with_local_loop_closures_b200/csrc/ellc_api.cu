@@ -1,0 +1,569 @@
+// ellc_api.cu -- C-ABI implementation (include/ellc_gn.h): handle, device pools, batching and launch orchestration.
+//
+// Device memory layout (all pools are slot-major, one cudaMalloc each):
+//   frames     img : u8   pyramid levels 0..3 concatenated (cv::pyrDown dims)          slot stride = geo.img_off[4]
+//              tex : u32  packed texels, level windows concatenated                    slot stride = geo.win_off[4]
+//   keyframes  img : u8   as frames
+//              depth, var : f32 level windows concatenated                             slot stride = geo.win_off[4]
+//              mask : u8  level windows                                                  "
+//              rec  : SelRec[ ] compacted selected pixels, level l starts at win_off[l]  "
+//              count[4], rowcount / rowoff scratch
+// Uploads only mark slots dirty; the pyramid / texel / selection kernels run batched over all dirty slots right before
+// the next consumer (track, evaluate, read-back) -- a whole batch costs 4 (frames) + 6 (keyframes) launches.
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "ellc_internal.h"
+#include "ellc_lie.cuh"
+
+using namespace ellc;
+
+struct ellc_handle {
+    ellc_config cfg;
+    Geometry geo;
+    LevelK K[kLevels];
+    int rows_total;
+    cudaStream_t stream;
+    cudaEvent_t ev0, ev1;
+    bool ev_valid;
+    // pools
+    uint8_t* fr_img; uint32_t* fr_tex;
+    uint8_t* kf_img; float* kf_depth; float* kf_var; uint8_t* kf_mask; SelRec* kf_rec;
+    int* kf_count; int* kf_rowcount; int* kf_rowoff;
+    std::vector<uint8_t> fr_state, kf_state;          // 0 empty, 1 image present (dirty), 2 prepared
+    std::vector<int> fr_dirty, kf_dirty;
+    // staging
+    int* d_slots; int slots_cap;
+    ellc_pair* d_pairs; ellc_result* d_results; int pairs_cap;
+    ellc_iter_trace* d_trace; int64_t trace_cap;
+    float* d_small;                                    // 128 floats in/out for solve_update
+    float* d_weight; int64_t weight_cap;
+    void* h_pin; size_t pin_cap, pin_used;             // pinned bump arena for small H2D payloads
+    std::string err;
+    int64_t launches;
+};
+
+static thread_local std::string g_create_err;
+
+#define CU_TRY(h, call)                                                                              \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess) {                                                                    \
+            (h)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                          \
+            return ELLC_ERR_CUDA;                                                                    \
+        }                                                                                            \
+    } while (0)
+
+static void build_geometry(const ellc_config& c, Geometry& g) {
+    g.width = c.width; g.height = c.height;
+    int pw = c.width, ph = c.height;
+    g.img_off[0] = 0; g.win_off[0] = 0;
+    for (int l = 0; l < kLevels; ++l) {
+        g.pyr_w[l] = pw; g.pyr_h[l] = ph;
+        g.cols[l] = c.width >> l; g.rows[l] = c.height >> l;
+        g.img_off[l + 1] = g.img_off[l] + (int64_t)pw * ph;
+        g.win_off[l + 1] = g.win_off[l] + (int64_t)g.cols[l] * g.rows[l];
+        pw = (pw + 1) / 2; ph = (ph + 1) / 2;
+    }
+}
+
+// GetIntrinsic, src/UserDefinedFunc.cpp:33-49
+static void build_intrinsics(const ellc_config& c, LevelK K[kLevels]) {
+    for (int l = 0; l < kLevels; ++l) {
+        const double s = (double)(1 << l);
+        K[l].fx = (float)(c.fx / s); K[l].fy = (float)(c.fy / s);
+        K[l].cx = (float)(c.cx / s); K[l].cy = (float)(c.cy / s);
+        K[l].ifx = 1.0f / K[l].fx; K[l].ify = 1.0f / K[l].fy;
+        K[l].fy_ifx = K[l].fy / K[l].fx; K[l].fx_ify = K[l].fx / K[l].fy;
+    }
+}
+
+extern "C" {
+
+const char* ellc_version(void) { return "ellc-gn-b200 0.1 (sm_100a)"; }
+
+void ellc_default_config(ellc_config* c, int32_t width, int32_t height) {
+    std::memset(c, 0, sizeof(*c));
+    c->width = width; c->height = height;
+    c->fx = 0.8f * width; c->fy = 0.8f * width; c->cx = width / 2.0f; c->cy = height / 2.0f;
+    c->max_iter[0] = 4; c->max_iter[1] = 7; c->max_iter[2] = 9; c->max_iter[3] = 12;      // src/main.cpp:34
+    c->huber_d = 3.0f; c->camera_pixel_noise_2 = 4.0f * 4.0f;                             // src/ExternVariable.h:148-149
+    c->weight[0] = c->weight[1] = c->weight[2] = 100000.0f;                               // :76
+    c->weight[3] = c->weight[4] = c->weight[5] = 10000.0f;
+    c->stop_threshold = 1.0f;                                                             // src/ImageFunc.cpp:251
+    c->arithmetic = ELLC_ARITH_FAST;
+    c->jacobian_at_warped = 0;
+    c->max_keyframes = 8; c->max_frames = 64;
+    c->ctas_per_pair = 0; c->device = 0;
+}
+
+const char* ellc_last_error_string(const ellc_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int ellc_destroy(ellc_handle* h) {
+    if (!h) return ELLC_OK;
+    cudaSetDevice(h->cfg.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaFree(h->fr_img); cudaFree(h->fr_tex); cudaFree(h->kf_img); cudaFree(h->kf_depth); cudaFree(h->kf_var);
+    cudaFree(h->kf_mask); cudaFree(h->kf_rec); cudaFree(h->kf_count); cudaFree(h->kf_rowcount); cudaFree(h->kf_rowoff);
+    cudaFree(h->d_slots); cudaFree(h->d_pairs); cudaFree(h->d_results); cudaFree(h->d_trace); cudaFree(h->d_small);
+    cudaFree(h->d_weight);
+    if (h->h_pin) cudaFreeHost(h->h_pin);
+    if (h->ev_valid) { cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); }
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return ELLC_OK;
+}
+
+int ellc_create(const ellc_config* cfg, ellc_handle** out) {
+    if (!cfg || !out) { g_create_err = "null argument"; return ELLC_ERR_INVALID; }
+    *out = nullptr;
+    if (cfg->width < 16 || cfg->height < 16 || cfg->width > 65535 || cfg->height > 65535 || cfg->max_keyframes < 1 ||
+        cfg->max_frames < 1) { g_create_err = "unsupported size / slot count"; return ELLC_ERR_INVALID; }
+    if (cfg->jacobian_at_warped) { g_create_err = "jacobian_at_warped (Pyramid.cpp variant) is not built yet"; return ELLC_ERR_INVALID; }
+    for (int l = 0; l < kLevels; ++l)
+        if (cfg->max_iter[l] < 0) { g_create_err = "negative max_iter"; return ELLC_ERR_INVALID; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= cfg->device) {
+        g_create_err = std::string("no usable CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e);
+        return ELLC_ERR_CUDA;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess || prop.major < 10) {
+        g_create_err = "device is not sm_100-class (this library carries sm_100a code only)";
+        return ELLC_ERR_CUDA;
+    }
+    ellc_handle* h = new (std::nothrow) ellc_handle();
+    if (!h) { g_create_err = "out of host memory"; return ELLC_ERR_INVALID; }
+    h->cfg = *cfg;
+    build_geometry(*cfg, h->geo);
+    build_intrinsics(*cfg, h->K);
+    h->rows_total = 0;
+    for (int l = 0; l < kLevels; ++l) h->rows_total += h->geo.rows[l];
+    h->fr_state.assign(cfg->max_frames, 0);
+    h->kf_state.assign(cfg->max_keyframes, 0);
+    h->launches = 0;
+#define CR_TRY(call)                                                                                 \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess) {                                                                    \
+            g_create_err = std::string(#call) + ": " + cudaGetErrorString(e__);                      \
+            ellc_destroy(h);                                                                         \
+            return ELLC_ERR_CUDA;                                                                    \
+        }                                                                                            \
+    } while (0)
+    CR_TRY(cudaSetDevice(cfg->device));
+    CR_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CR_TRY(cudaEventCreate(&h->ev0));
+    CR_TRY(cudaEventCreate(&h->ev1));
+    h->ev_valid = true;
+    const int64_t img = h->geo.img_off[kLevels], win = h->geo.win_off[kLevels];
+    const int64_t nf = cfg->max_frames, nk = cfg->max_keyframes;
+    CR_TRY(cudaMalloc(&h->fr_img, nf * img));
+    CR_TRY(cudaMalloc(&h->fr_tex, nf * win * sizeof(uint32_t)));
+    CR_TRY(cudaMalloc(&h->kf_img, nk * img));
+    CR_TRY(cudaMalloc(&h->kf_depth, nk * win * sizeof(float)));
+    CR_TRY(cudaMalloc(&h->kf_var, nk * win * sizeof(float)));
+    CR_TRY(cudaMalloc(&h->kf_mask, nk * win));
+    CR_TRY(cudaMalloc(&h->kf_rec, nk * win * sizeof(SelRec)));
+    CR_TRY(cudaMalloc(&h->kf_count, nk * kLevels * sizeof(int)));
+    CR_TRY(cudaMalloc(&h->kf_rowcount, nk * h->rows_total * sizeof(int)));
+    CR_TRY(cudaMalloc(&h->kf_rowoff, nk * h->rows_total * sizeof(int)));
+    h->slots_cap = (int)(nf > nk ? nf : nk);
+    CR_TRY(cudaMalloc(&h->d_slots, 2 * h->slots_cap * sizeof(int)));
+    CR_TRY(cudaMalloc(&h->d_small, 128 * sizeof(float)));
+    h->pin_cap = 1 << 20;
+    CR_TRY(cudaMallocHost(&h->h_pin, h->pin_cap));
+    h->pin_used = 0;
+    CR_TRY(cudaMemsetAsync(h->kf_count, 0, nk * kLevels * sizeof(int), h->stream));
+    CR_TRY(cudaStreamSynchronize(h->stream));
+#undef CR_TRY
+    *out = h;
+    return ELLC_OK;
+}
+
+}  // extern "C"
+
+// ---- internal helpers ------------------------------------------------------------------------------------------------
+// Copy a small host payload to the device through the pinned arena (no implicit host/device serialisation).
+static int stage_h2d(ellc_handle* h, void* dst, const void* src, size_t bytes) {
+    if (bytes > h->pin_cap / 2) {           // large payload: plain (staged) async copy
+        CU_TRY(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
+        return ELLC_OK;
+    }
+    const size_t aligned = (bytes + 255) & ~(size_t)255;
+    if (h->pin_used + aligned > h->pin_cap) {
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+        h->pin_used = 0;
+    }
+    void* p = (char*)h->h_pin + h->pin_used;
+    std::memcpy(p, src, bytes);
+    h->pin_used += aligned;
+    CU_TRY(h, cudaMemcpyAsync(dst, p, bytes, cudaMemcpyHostToDevice, h->stream));
+    return ELLC_OK;
+}
+
+static int ensure_pairs_cap(ellc_handle* h, int n, bool want_trace) {
+    if (n > h->pairs_cap) {
+        cudaFree(h->d_pairs); cudaFree(h->d_results);
+        h->d_pairs = nullptr; h->d_results = nullptr; h->pairs_cap = 0;
+        int cap = n < 256 ? 256 : n;
+        CU_TRY(h, cudaMalloc(&h->d_pairs, (size_t)cap * sizeof(ellc_pair)));
+        CU_TRY(h, cudaMalloc(&h->d_results, (size_t)cap * sizeof(ellc_result)));
+        h->pairs_cap = cap;
+    }
+    if (want_trace) {
+        const int64_t need = (int64_t)n * kLevels * ELLC_MAX_TRACE_ITERS;
+        if (need > h->trace_cap) {
+            cudaFree(h->d_trace); h->d_trace = nullptr; h->trace_cap = 0;
+            CU_TRY(h, cudaMalloc(&h->d_trace, (size_t)need * sizeof(ellc_iter_trace)));
+            h->trace_cap = need;
+        }
+    }
+    return ELLC_OK;
+}
+
+static int prepare_frames_impl(ellc_handle* h, int n, const int* slots) {
+    if (n <= 0) return ELLC_OK;
+    int rc = stage_h2d(h, h->d_slots, slots, (size_t)n * sizeof(int));
+    if (rc) return rc;
+    h->launches += launch_pyramid(h->stream, h->fr_img, h->geo.img_off[kLevels], h->d_slots, n, h->geo);
+    h->launches += launch_pack_tex(h->stream, h->fr_img, h->geo.img_off[kLevels], h->fr_tex, h->geo.win_off[kLevels],
+                                   h->d_slots, n, h->geo);
+    CU_TRY(h, cudaGetLastError());
+    for (int i = 0; i < n; ++i) h->fr_state[slots[i]] = 2;
+    return ELLC_OK;
+}
+
+static int prepare_keyframes_impl(ellc_handle* h, int n, const int* slots) {
+    if (n <= 0) return ELLC_OK;
+    int* d_slots = h->d_slots + h->slots_cap;
+    int rc = stage_h2d(h, d_slots, slots, (size_t)n * sizeof(int));
+    if (rc) return rc;
+    h->launches += launch_pyramid(h->stream, h->kf_img, h->geo.img_off[kLevels], d_slots, n, h->geo);
+    h->launches += launch_select(h->stream, h->kf_depth, h->kf_var, h->geo.win_off[kLevels], h->kf_img,
+                                 h->geo.img_off[kLevels], h->kf_mask, h->kf_rowcount, h->kf_rowoff, h->kf_count,
+                                 h->kf_rec, d_slots, n, h->geo);
+    CU_TRY(h, cudaGetLastError());
+    for (int i = 0; i < n; ++i) h->kf_state[slots[i]] = 2;
+    return ELLC_OK;
+}
+
+static int flush_dirty(ellc_handle* h) {
+    if (!h->fr_dirty.empty()) {
+        std::vector<int> s;
+        for (int v : h->fr_dirty) if (h->fr_state[v] == 1) { s.push_back(v); h->fr_state[v] = 3; }
+        for (int v : s) h->fr_state[v] = 1;
+        h->fr_dirty.clear();
+        int rc = prepare_frames_impl(h, (int)s.size(), s.data());
+        if (rc) return rc;
+    }
+    if (!h->kf_dirty.empty()) {
+        std::vector<int> s;
+        for (int v : h->kf_dirty) if (h->kf_state[v] == 1) { s.push_back(v); h->kf_state[v] = 3; }
+        for (int v : s) h->kf_state[v] = 1;
+        h->kf_dirty.clear();
+        int rc = prepare_keyframes_impl(h, (int)s.size(), s.data());
+        if (rc) return rc;
+    }
+    return ELLC_OK;
+}
+
+static void fill_params(const ellc_handle* h, TrackParams& p) {
+    std::memset(&p, 0, sizeof(p));
+    p.geo = h->geo;
+    for (int l = 0; l < kLevels; ++l) { p.K[l] = h->K[l]; p.max_iter[l] = h->cfg.max_iter[l]; }
+    p.huber_half = h->cfg.huber_d / 2;
+    p.noise2 = h->cfg.camera_pixel_noise_2;
+    for (int i = 0; i < 6; ++i) p.weight[i] = h->cfg.weight[i];
+    p.stop_threshold = h->cfg.stop_threshold;
+    p.jacobian_at_warped = h->cfg.jacobian_at_warped;
+    p.tex_pool = h->fr_tex; p.tex_slot_stride = h->geo.win_off[kLevels];
+    p.rec_pool = h->kf_rec; p.rec_slot_stride = h->geo.win_off[kLevels];
+    p.count_pool = h->kf_count;
+    p.level_hi = kLevels - 1; p.level_lo = 0;
+}
+
+static int pick_cluster(const ellc_handle* h, int n) {
+    int c = h->cfg.ctas_per_pair;
+    if (c == 1 || c == 2 || c == 4 || c == 8) return c;
+    if (n >= 148) return 1;
+    c = 8;
+    while (c > 1 && (int64_t)n * c > 296) c >>= 1;
+    return c;
+}
+
+static int validate_pairs(ellc_handle* h, int n, const ellc_pair* pairs) {
+    for (int i = 0; i < n; ++i) {
+        const ellc_pair& q = pairs[i];
+        if (q.kf_slot < 0 || q.kf_slot >= h->cfg.max_keyframes || q.frame_slot < 0 || q.frame_slot >= h->cfg.max_frames) {
+            h->err = "pair references a slot out of range";
+            return ELLC_ERR_INVALID;
+        }
+        if (h->kf_state[q.kf_slot] == 0 || h->fr_state[q.frame_slot] == 0) {
+            h->err = "pair references a slot that was never uploaded";
+            return ELLC_ERR_NOT_READY;
+        }
+        if (q.flags & (ELLC_PAIR_CONST_WEIGHT | ELLC_PAIR_SAVE_WEIGHTS)) {
+            h->err = "constant-weight loop-closure variant is not built yet";
+            return ELLC_ERR_INVALID;
+        }
+    }
+    return ELLC_OK;
+}
+
+static int track_launch(ellc_handle* h, int n, const ellc_pair* pairs, bool want_trace) {
+    int rc = validate_pairs(h, n, pairs);
+    if (rc) return rc;
+    CU_TRY(h, cudaSetDevice(h->cfg.device));
+    rc = flush_dirty(h);
+    if (rc) return rc;
+    rc = ensure_pairs_cap(h, n, want_trace);
+    if (rc) return rc;
+    rc = stage_h2d(h, h->d_pairs, pairs, (size_t)n * sizeof(ellc_pair));
+    if (rc) return rc;
+    if (want_trace) CU_TRY(h, cudaMemsetAsync(h->d_trace, 0, (size_t)n * kLevels * ELLC_MAX_TRACE_ITERS * sizeof(ellc_iter_trace), h->stream));
+    TrackParams p;
+    fill_params(h, p);
+    p.pairs = h->d_pairs; p.results = h->d_results; p.trace = want_trace ? h->d_trace : nullptr; p.n_pairs = n;
+    CU_TRY(h, cudaEventRecord(h->ev0, h->stream));
+    const int l = launch_track(h->stream, p, pick_cluster(h, n), h->cfg.arithmetic == ELLC_ARITH_STRICT);
+    if (l < 0) { h->err = std::string("track kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()); return ELLC_ERR_CUDA; }
+    h->launches += l;
+    CU_TRY(h, cudaEventRecord(h->ev1, h->stream));
+    CU_TRY(h, cudaGetLastError());
+    return ELLC_OK;
+}
+
+extern "C" {
+
+int ellc_upload_frame(ellc_handle* h, int32_t slot, const uint8_t* image) {
+    if (!h) return ELLC_ERR_INVALID;
+    if (!image || slot < 0 || slot >= h->cfg.max_frames) { h->err = "bad frame slot / null image"; return ELLC_ERR_INVALID; }
+    CU_TRY(h, cudaSetDevice(h->cfg.device));
+    CU_TRY(h, cudaMemcpyAsync(h->fr_img + (int64_t)slot * h->geo.img_off[kLevels], image, (size_t)h->geo.img_off[1],
+                              cudaMemcpyHostToDevice, h->stream));
+    h->fr_state[slot] = 1;
+    h->fr_dirty.push_back(slot);
+    return ELLC_OK;
+}
+
+int ellc_upload_keyframe(ellc_handle* h, int32_t slot, const uint8_t* image, const float* const depth[ELLC_LEVELS],
+                         const float* const var[ELLC_LEVELS]) {
+    if (!h) return ELLC_ERR_INVALID;
+    if (!image || !depth || !var || slot < 0 || slot >= h->cfg.max_keyframes) { h->err = "bad keyframe slot / null pointer"; return ELLC_ERR_INVALID; }
+    for (int l = 0; l < kLevels; ++l) if (!depth[l] || !var[l]) { h->err = "null depth/var level"; return ELLC_ERR_INVALID; }
+    CU_TRY(h, cudaSetDevice(h->cfg.device));
+    CU_TRY(h, cudaMemcpyAsync(h->kf_img + (int64_t)slot * h->geo.img_off[kLevels], image, (size_t)h->geo.img_off[1],
+                              cudaMemcpyHostToDevice, h->stream));
+    const int64_t win = h->geo.win_off[kLevels];
+    for (int l = 0; l < kLevels; ++l) {
+        const size_t bytes = (size_t)(h->geo.win_off[l + 1] - h->geo.win_off[l]) * sizeof(float);
+        CU_TRY(h, cudaMemcpyAsync(h->kf_depth + slot * win + h->geo.win_off[l], depth[l], bytes, cudaMemcpyHostToDevice, h->stream));
+        CU_TRY(h, cudaMemcpyAsync(h->kf_var + slot * win + h->geo.win_off[l], var[l], bytes, cudaMemcpyHostToDevice, h->stream));
+    }
+    h->kf_state[slot] = 1;
+    h->kf_dirty.push_back(slot);
+    return ELLC_OK;
+}
+
+int ellc_frame_image_devptr(ellc_handle* h, int32_t slot, uint8_t** image) {
+    if (!h || !image || slot < 0 || slot >= h->cfg.max_frames) return ELLC_ERR_INVALID;
+    *image = h->fr_img + (int64_t)slot * h->geo.img_off[kLevels];
+    return ELLC_OK;
+}
+
+int ellc_keyframe_devptrs(ellc_handle* h, int32_t slot, uint8_t** image, float** depth, float** var,
+                          int64_t level_offsets[ELLC_LEVELS + 1]) {
+    if (!h || slot < 0 || slot >= h->cfg.max_keyframes) return ELLC_ERR_INVALID;
+    const int64_t win = h->geo.win_off[kLevels];
+    if (image) *image = h->kf_img + (int64_t)slot * h->geo.img_off[kLevels];
+    if (depth) *depth = h->kf_depth + slot * win;
+    if (var) *var = h->kf_var + slot * win;
+    if (level_offsets) for (int l = 0; l <= kLevels; ++l) level_offsets[l] = h->geo.win_off[l];
+    return ELLC_OK;
+}
+
+int ellc_prepare_frames(ellc_handle* h, int32_t n, const int32_t* slots) {
+    if (!h || (n > 0 && !slots) || n > h->cfg.max_frames) return ELLC_ERR_INVALID;
+    for (int i = 0; i < n; ++i) if (slots[i] < 0 || slots[i] >= h->cfg.max_frames) { h->err = "frame slot out of range"; return ELLC_ERR_INVALID; }
+    CU_TRY(h, cudaSetDevice(h->cfg.device));
+    return prepare_frames_impl(h, n, slots);
+}
+
+int ellc_prepare_keyframes(ellc_handle* h, int32_t n, const int32_t* slots) {
+    if (!h || (n > 0 && !slots) || n > h->cfg.max_keyframes) return ELLC_ERR_INVALID;
+    for (int i = 0; i < n; ++i) if (slots[i] < 0 || slots[i] >= h->cfg.max_keyframes) { h->err = "keyframe slot out of range"; return ELLC_ERR_INVALID; }
+    CU_TRY(h, cudaSetDevice(h->cfg.device));
+    return prepare_keyframes_impl(h, n, slots);
+}
+
+int ellc_synchronize(ellc_handle* h) {
+    if (!h) return ELLC_ERR_INVALID;
+    CU_TRY(h, cudaSetDevice(h->cfg.device));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    h->pin_used = 0;
+    return ELLC_OK;
+}
+
+int ellc_track_batch_async(ellc_handle* h, int32_t n, const ellc_pair* pairs, const ellc_result** device_results) {
+    if (!h) return ELLC_ERR_INVALID;
+    if (n < 0 || (n > 0 && !pairs)) { h->err = "bad pair list"; return ELLC_ERR_INVALID; }
+    int rc = track_launch(h, n, pairs, false);
+    if (rc) return rc;
+    if (device_results) *device_results = h->d_results;
+    return ELLC_OK;
+}
+
+int ellc_track_batch(ellc_handle* h, int32_t n, const ellc_pair* pairs, ellc_result* results, ellc_iter_trace* trace) {
+    if (!h) return ELLC_ERR_INVALID;
+    if (n < 0 || (n > 0 && (!pairs || !results))) { h->err = "bad pair list / null results"; return ELLC_ERR_INVALID; }
+    if (n == 0) return ELLC_OK;
+    int rc = track_launch(h, n, pairs, trace != nullptr);
+    if (rc) return rc;
+    CU_TRY(h, cudaMemcpyAsync(results, h->d_results, (size_t)n * sizeof(ellc_result), cudaMemcpyDeviceToHost, h->stream));
+    if (trace) CU_TRY(h, cudaMemcpyAsync(trace, h->d_trace, (size_t)n * kLevels * ELLC_MAX_TRACE_ITERS * sizeof(ellc_iter_trace),
+                                         cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    h->pin_used = 0;
+    return ELLC_OK;
+}
+
+int ellc_gn_evaluate(ellc_handle* h, int32_t kf_slot, int32_t frame_slot, int32_t level, const float pose[6],
+                     ellc_iter_trace* out, float* weight_image) {
+    if (!h) return ELLC_ERR_INVALID;
+    if (!pose || !out || level < 0 || level >= kLevels) { h->err = "bad evaluate arguments"; return ELLC_ERR_INVALID; }
+    ellc_pair pr;
+    pr.kf_slot = kf_slot; pr.frame_slot = frame_slot; pr.flags = 0;
+    for (int i = 0; i < 6; ++i) pr.init_pose[i] = pose[i];
+    int rc = validate_pairs(h, 1, &pr);
+    if (rc) return rc;
+    CU_TRY(h, cudaSetDevice(h->cfg.device));
+    rc = flush_dirty(h);
+    if (rc) return rc;
+    rc = ensure_pairs_cap(h, 1, true);
+    if (rc) return rc;
+    rc = stage_h2d(h, h->d_pairs, &pr, sizeof(pr));
+    if (rc) return rc;
+    const int64_t npx = (int64_t)h->geo.cols[level] * h->geo.rows[level];
+    if (weight_image) {
+        if (npx > h->weight_cap) {
+            cudaFree(h->d_weight); h->d_weight = nullptr; h->weight_cap = 0;
+            CU_TRY(h, cudaMalloc(&h->d_weight, (size_t)h->geo.win_off[1] * sizeof(float)));
+            h->weight_cap = h->geo.win_off[1];
+        }
+        CU_TRY(h, cudaMemsetAsync(h->d_weight, 0, (size_t)npx * sizeof(float), h->stream));
+    }
+    CU_TRY(h, cudaMemsetAsync(h->d_trace, 0, (size_t)kLevels * ELLC_MAX_TRACE_ITERS * sizeof(ellc_iter_trace), h->stream));
+    TrackParams p;
+    fill_params(h, p);
+    p.pairs = h->d_pairs; p.results = h->d_results; p.trace = h->d_trace; p.n_pairs = 1;
+    p.level_hi = p.level_lo = level; p.iter_limit = 1; p.no_update = 1;
+    p.weight_out = weight_image ? h->d_weight : nullptr;
+    const int l = launch_track(h->stream, p, pick_cluster(h, 1), h->cfg.arithmetic == ELLC_ARITH_STRICT);
+    if (l < 0) { h->err = std::string("track kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()); return ELLC_ERR_CUDA; }
+    h->launches += l;
+    CU_TRY(h, cudaMemcpyAsync(out, h->d_trace + (int64_t)level * ELLC_MAX_TRACE_ITERS, sizeof(ellc_iter_trace), cudaMemcpyDeviceToHost, h->stream));
+    if (weight_image) CU_TRY(h, cudaMemcpyAsync(weight_image, h->d_weight, (size_t)npx * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    h->pin_used = 0;
+    return ELLC_OK;
+}
+
+int ellc_solve_update(ellc_handle* h, const float H[36], const float b[6], const float pose_in[6], float pose_out[6],
+                      float delta[6], float* weighted_pose) {
+    if (!h) return ELLC_ERR_INVALID;
+    if (!H || !b || !pose_in || !pose_out || !delta || !weighted_pose) { h->err = "null argument"; return ELLC_ERR_INVALID; }
+    CU_TRY(h, cudaSetDevice(h->cfg.device));
+    float in[54], outv[14];
+    for (int i = 0; i < 36; ++i) in[i] = H[i];
+    for (int i = 0; i < 6; ++i) { in[36 + i] = b[i]; in[42 + i] = pose_in[i]; in[48 + i] = h->cfg.weight[i]; }
+    int rc = stage_h2d(h, h->d_small, in, sizeof(in));
+    if (rc) return rc;
+    h->launches += launch_solve_update(h->stream, h->d_small, h->d_small + 64);
+    CU_TRY(h, cudaMemcpyAsync(outv, h->d_small + 64, sizeof(outv), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    h->pin_used = 0;
+    for (int i = 0; i < 6; ++i) { pose_out[i] = outv[i]; delta[i] = outv[6 + i]; }
+    *weighted_pose = outv[12];
+    return ELLC_OK;
+}
+
+int ellc_level_dims(const ellc_handle* h, int32_t level, int32_t* pyr_w, int32_t* pyr_h, int32_t* cols, int32_t* rows) {
+    if (!h || level < 0 || level >= kLevels) return ELLC_ERR_INVALID;
+    if (pyr_w) *pyr_w = h->geo.pyr_w[level];
+    if (pyr_h) *pyr_h = h->geo.pyr_h[level];
+    if (cols) *cols = h->geo.cols[level];
+    if (rows) *rows = h->geo.rows[level];
+    return ELLC_OK;
+}
+
+int ellc_read_frame_level(ellc_handle* h, int32_t slot, int32_t level, uint8_t* image, float* gradx, float* grady) {
+    if (!h) return ELLC_ERR_INVALID;
+    if (slot < 0 || slot >= h->cfg.max_frames || level < 0 || level >= kLevels) { h->err = "bad slot/level"; return ELLC_ERR_INVALID; }
+    if (h->fr_state[slot] == 0) { h->err = "frame slot empty"; return ELLC_ERR_NOT_READY; }
+    CU_TRY(h, cudaSetDevice(h->cfg.device));
+    int rc = flush_dirty(h);
+    if (rc) return rc;
+    const Geometry& g = h->geo;
+    if (image) CU_TRY(h, cudaMemcpyAsync(image, h->fr_img + (int64_t)slot * g.img_off[kLevels] + g.img_off[level],
+                                         (size_t)g.pyr_w[level] * g.pyr_h[level], cudaMemcpyDeviceToHost, h->stream));
+    std::vector<uint32_t> tex;
+    const size_t npx = (size_t)g.cols[level] * g.rows[level];
+    if (gradx || grady) {
+        tex.resize(npx);
+        CU_TRY(h, cudaMemcpyAsync(tex.data(), h->fr_tex + (int64_t)slot * g.win_off[kLevels] + g.win_off[level], npx * 4,
+                                  cudaMemcpyDeviceToHost, h->stream));
+    }
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    h->pin_used = 0;
+    for (size_t i = 0; i < tex.size(); ++i) {           // unpack only: the differences were taken on the device
+        if (gradx) gradx[i] = 0.5f * (float)tex_gx2(tex[i]);
+        if (grady) grady[i] = 0.5f * (float)tex_gy2(tex[i]);
+    }
+    return ELLC_OK;
+}
+
+int ellc_read_keyframe_level(ellc_handle* h, int32_t slot, int32_t level, uint8_t* image, uint8_t* mask, int32_t* count) {
+    if (!h) return ELLC_ERR_INVALID;
+    if (slot < 0 || slot >= h->cfg.max_keyframes || level < 0 || level >= kLevels) { h->err = "bad slot/level"; return ELLC_ERR_INVALID; }
+    if (h->kf_state[slot] == 0) { h->err = "keyframe slot empty"; return ELLC_ERR_NOT_READY; }
+    CU_TRY(h, cudaSetDevice(h->cfg.device));
+    int rc = flush_dirty(h);
+    if (rc) return rc;
+    const Geometry& g = h->geo;
+    if (image) CU_TRY(h, cudaMemcpyAsync(image, h->kf_img + (int64_t)slot * g.img_off[kLevels] + g.img_off[level],
+                                         (size_t)g.pyr_w[level] * g.pyr_h[level], cudaMemcpyDeviceToHost, h->stream));
+    if (mask) CU_TRY(h, cudaMemcpyAsync(mask, h->kf_mask + (int64_t)slot * g.win_off[kLevels] + g.win_off[level],
+                                        (size_t)g.cols[level] * g.rows[level], cudaMemcpyDeviceToHost, h->stream));
+    if (count) CU_TRY(h, cudaMemcpyAsync(count, h->kf_count + slot * kLevels + level, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    h->pin_used = 0;
+    return ELLC_OK;
+}
+
+void ellc_concat_relative(const float a[6], const float b[6], float dest[6]) { concat_relative_f(a, b, dest); }
+void ellc_concat_origin(const float a[6], const float b[6], float dest[6]) { concat_origin_f(a, b, dest); }
+void ellc_se3_exp(const float pose[6], float T[16]) {
+    float Rt[12];
+    pose_to_rt_f(pose, Rt);
+    for (int i = 0; i < 12; ++i) T[i] = Rt[i];
+    T[12] = T[13] = T[14] = 0.f; T[15] = 1.f;
+}
+
+int64_t ellc_launch_count(const ellc_handle* h) { return h ? h->launches : 0; }
+void ellc_reset_launch_count(ellc_handle* h) { if (h) h->launches = 0; }
+void* ellc_stream(ellc_handle* h) { return h ? (void*)h->stream : nullptr; }
+float ellc_last_track_kernel_ms(ellc_handle* h) {
+    if (!h || !h->ev_valid) return -1.f;
+    float ms = -1.f;
+    if (cudaEventSynchronize(h->ev1) != cudaSuccess) return -1.f;
+    if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) != cudaSuccess) return -1.f;
+    return ms;
+}
+
+}  // extern "C"

@@ -1,0 +1,23 @@
+// ellc_internal.h -- launch wrappers shared between the translation units of libellc_gn.so (not part of the ABI).
+#pragma once
+
+#include "ellc_common.cuh"
+
+namespace ellc {
+
+// ellc_preprocess.cu -- each returns the number of kernels it launched
+int launch_pyramid(cudaStream_t st, uint8_t* img_pool, int64_t img_slot_stride, const int* d_slots, int n, const Geometry& geo);
+int launch_pack_tex(cudaStream_t st, const uint8_t* img_pool, int64_t img_slot_stride, uint32_t* tex_pool,
+                    int64_t tex_slot_stride, const int* d_slots, int n, const Geometry& geo);
+int launch_select(cudaStream_t st, const float* depth_pool, const float* var_pool, int64_t win_slot_stride,
+                  const uint8_t* img_pool, int64_t img_slot_stride, uint8_t* mask_pool, int* rowcount_pool,
+                  int* rowoff_pool, int* count_pool, SelRec* rec_pool, const int* d_slots, int n, const Geometry& geo);
+
+// ellc_track.cu
+// Launches the GN tracking kernel for p.n_pairs pairs with `cluster` CTAs per pair.  Returns kernels launched (1) or a
+// negative value on launch-configuration failure (cudaGetLastError carries the reason).
+int launch_track(cudaStream_t st, const TrackParams& p, int cluster, bool strict);
+// single-thread kernel running solve_update_f on the device (ellc_solve_update)
+int launch_solve_update(cudaStream_t st, const float* d_in /*H36 b6 pose6 weight6*/, float* d_out /*pose6 delta6 wp1 ok1*/);
+
+}  // namespace ellc

@@ -1,0 +1,261 @@
+// ellc_preprocess.cu -- per-frame and per-keyframe preparation kernels (sm_100a).
+//
+//   K1  pyrdown_u8_kernel   frame::constructImagePyramids -> cv::pyrDown x3      (src/Frame.cpp:170-182)
+//   K2  pack_tex_kernel     frame::calculateGradient for every level            (src/Frame.cpp:185-285), fused with the
+//                           intensity into one 32-bit texel per pixel (ellc_common.cuh) so that a bilinear tap of the GN
+//                           kernel is a single gather
+//   K3  select_*_kernel     frame::calculateNonZeroDepthPts: mask = depth > 0, count (src/Frame.cpp:295-301), plus an
+//                           order-preserving compaction of the selected pixels into SelRec lists (raster order)
+//
+// All kernels are batched over slots (blockIdx.z / blockIdx.y) so that a whole batch of frames costs 4 launches.
+#include "ellc_internal.h"
+
+namespace ellc {
+
+// BORDER_REFLECT_101 with repeated folding for tiny images
+__device__ __forceinline__ int reflect101(int i, int n) {
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) i = (i < 0) ? -i : 2 * n - 2 - i;
+    return i;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K1: one pyrDown step for a batch of slots.  32x8 output tile per CTA; the (67 x 19) source footprint is staged in
+// shared memory, filtered horizontally into int rows, then vertically; out = (sum + 128) >> 8 (exact integer).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int PD_TX = 32, PD_TY = 8;
+constexpr int PD_SW = 2 * PD_TX + 3, PD_SH = 2 * PD_TY + 3;
+
+__global__ void __launch_bounds__(PD_TX * PD_TY)
+pyrdown_u8_kernel(uint8_t* __restrict__ pool, int64_t slot_stride, const int* __restrict__ slots,
+                  int64_t src_off, int sw, int sh, int64_t dst_off, int dw, int dh) {
+    __shared__ uint8_t s_src[PD_SH][PD_SW + 1];
+    __shared__ int s_row[PD_SH][PD_TX];
+    uint8_t* base = pool + (int64_t)slots[blockIdx.z] * slot_stride;
+    const uint8_t* __restrict__ src = base + src_off;
+    uint8_t* __restrict__ dst = base + dst_off;
+    const int ox = blockIdx.x * PD_TX, oy = blockIdx.y * PD_TY;
+    const int tid = threadIdx.y * PD_TX + threadIdx.x;
+    const int sx0 = 2 * ox - 2, sy0 = 2 * oy - 2;
+    for (int i = tid; i < PD_SW * PD_SH; i += PD_TX * PD_TY) {
+        const int ly = i / PD_SW, lx = i - ly * PD_SW;
+        const int gy = reflect101(sy0 + ly, sh), gx = reflect101(sx0 + lx, sw);
+        s_src[ly][lx] = src[(int64_t)gy * sw + gx];
+    }
+    __syncthreads();
+    for (int i = tid; i < PD_SH * PD_TX; i += PD_TX * PD_TY) {
+        const int ly = i / PD_TX, lx = i - ly * PD_TX;
+        const uint8_t* r = &s_src[ly][2 * lx];
+        s_row[ly][lx] = r[0] + 4 * r[1] + 6 * r[2] + 4 * r[3] + r[4];
+    }
+    __syncthreads();
+    const int x = ox + threadIdx.x, y = oy + threadIdx.y;
+    if (x < dw && y < dh) {
+        const int ly = 2 * threadIdx.y, lx = threadIdx.x;
+        const int acc = s_row[ly][lx] + 4 * s_row[ly + 1][lx] + 6 * s_row[ly + 2][lx] + 4 * s_row[ly + 3][lx] + s_row[ly + 4][lx];
+        dst[(int64_t)y * dw + x] = (uint8_t)((acc + 128) >> 8);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K2: packed texels for all levels of a batch of frame slots.  One thread per pixel of the concatenated level windows.
+// Border rule of src/Frame.cpp:222-283: one-sided, un-halved differences on the 1-px border of the (cols x rows) window.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pack_tex_kernel(const uint8_t* __restrict__ img_pool, int64_t img_slot_stride, uint32_t* __restrict__ tex_pool,
+                int64_t tex_slot_stride, const int* __restrict__ slots, Geometry geo) {
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= geo.win_off[kLevels]) return;
+    int level = 0;
+#pragma unroll
+    for (int l = 1; l < kLevels; ++l) level += (gid >= geo.win_off[l]);
+    const int cols = geo.cols[level], rows = geo.rows[level], stride = geo.pyr_w[level];
+    const int local = (int)(gid - geo.win_off[level]);
+    const int y = local / cols, x = local - y * cols;
+    const int slot = slots[blockIdx.y];
+    const uint8_t* __restrict__ img = img_pool + (int64_t)slot * img_slot_stride + geo.img_off[level];
+    const uint8_t* r = img + (int64_t)y * stride;
+    const int c = r[x];
+    int gx2, gy2;
+    if (x == 0) gx2 = 2 * ((int)r[1] - c);
+    else if (x == cols - 1) gx2 = 2 * (c - (int)r[x - 1]);
+    else gx2 = (int)r[x + 1] - (int)r[x - 1];
+    if (y == 0) gy2 = 2 * ((int)r[stride + x] - c);
+    else if (y == rows - 1) gy2 = 2 * (c - (int)r[x - stride]);
+    else gy2 = (int)r[stride + x] - (int)r[x - stride];
+    tex_pool[(int64_t)slot * tex_slot_stride + gid] = tex_pack(c, gx2, gy2);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K3: selection.  Pass A counts per row and writes the mask, pass B scans the row counts per level, pass C writes the
+// compacted SelRec lists in raster order (deterministic).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int SEL_T = 128;
+
+__device__ __forceinline__ void row_to_level(const Geometry& geo, int grow, int& level, int& y) {
+    level = 0;
+    int base = 0;
+    bool open = true;
+#pragma unroll
+    for (int l = 0; l < kLevels - 1; ++l) {
+        const int next = base + geo.rows[l];
+        if (open && grow >= next) { base = next; level = l + 1; }
+        else open = false;
+    }
+    y = grow - base;
+}
+
+__global__ void __launch_bounds__(SEL_T)
+select_count_kernel(const float* __restrict__ depth_pool, int64_t win_slot_stride, uint8_t* __restrict__ mask_pool,
+                    int* __restrict__ rowcount_pool, int rows_total, const int* __restrict__ slots, Geometry geo) {
+    int level, y;
+    row_to_level(geo, blockIdx.x, level, y);
+    const int slot = slots[blockIdx.y];
+    const int cols = geo.cols[level];
+    const int64_t off = (int64_t)slot * win_slot_stride + geo.win_off[level] + (int64_t)y * cols;
+    const float* __restrict__ d = depth_pool + off;
+    uint8_t* __restrict__ m = mask_pool + off;
+    int cnt = 0;
+    for (int x = threadIdx.x; x < cols; x += SEL_T) {
+        const bool sel = d[x] > 0.0f;             // NaN compares false -> unselected, as cv::compare
+        m[x] = sel ? 255 : 0;
+        cnt += sel;
+    }
+    __shared__ int s_w[SEL_T / 32];
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < SEL_T / 32; ++w) t += s_w[w];
+        rowcount_pool[(int64_t)slot * rows_total + blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+select_scan_kernel(const int* __restrict__ rowcount_pool, int* __restrict__ rowoff_pool, int* __restrict__ count_pool,
+                   int rows_total, const int* __restrict__ slots, Geometry geo) {
+    const int level = blockIdx.x;
+    const int slot = slots[blockIdx.y];
+    int base = 0;
+    for (int l = 0; l < level; ++l) base += geo.rows[l];
+    const int rows = geo.rows[level];
+    const int* __restrict__ rc = rowcount_pool + (int64_t)slot * rows_total + base;
+    int* __restrict__ ro = rowoff_pool + (int64_t)slot * rows_total + base;
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int start = 0; start < rows; start += 1024) {
+        const int i = start + threadIdx.x;
+        const int v = (i < rows) ? rc[i] : 0;
+        int inc = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += n;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_warp[lane];
+            for (int o = 1; o < 32; o <<= 1) {
+                const int n = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += n;
+            }
+            s_warp[lane] = w;                      // inclusive scan of warp totals
+        }
+        __syncthreads();
+        const int carry = s_carry;
+        const int wbase = (warp == 0) ? 0 : s_warp[warp - 1];
+        if (i < rows) ro[i] = carry + wbase + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = carry + s_warp[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) count_pool[slot * kLevels + level] = s_carry;
+}
+
+__global__ void __launch_bounds__(SEL_T)
+select_write_kernel(const float* __restrict__ depth_pool, const float* __restrict__ var_pool, int64_t win_slot_stride,
+                    const uint8_t* __restrict__ img_pool, int64_t img_slot_stride, const int* __restrict__ rowoff_pool,
+                    int rows_total, SelRec* __restrict__ rec_pool, const int* __restrict__ slots, Geometry geo) {
+    int level, y;
+    row_to_level(geo, blockIdx.x, level, y);
+    const int slot = slots[blockIdx.y];
+    const int cols = geo.cols[level];
+    const int64_t off = (int64_t)slot * win_slot_stride + geo.win_off[level] + (int64_t)y * cols;
+    const float* __restrict__ d = depth_pool + off;
+    const float* __restrict__ v = var_pool + off;
+    const uint8_t* __restrict__ img = img_pool + (int64_t)slot * img_slot_stride + geo.img_off[level] + (int64_t)y * geo.pyr_w[level];
+    SelRec* __restrict__ out = rec_pool + (int64_t)slot * win_slot_stride + geo.win_off[level] +
+                               rowoff_pool[(int64_t)slot * rows_total + blockIdx.x];
+    __shared__ int s_w[SEL_T / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int running = 0;
+    for (int start = 0; start < cols; start += SEL_T) {
+        const int x = start + threadIdx.x;
+        float dep = 0.f;
+        bool sel = false;
+        if (x < cols) { dep = d[x]; sel = dep > 0.0f; }
+        const unsigned bal = __ballot_sync(0xffffffffu, sel);
+        const int rank_in_warp = __popc(bal & ((1u << lane) - 1u));
+        if (lane == 0) s_w[warp] = __popc(bal);
+        __syncthreads();
+        int wbase = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < SEL_T / 32; ++w) {
+            const int c = s_w[w];
+            if (w < warp) wbase += c;
+            total += c;
+        }
+        if (sel) {
+            SelRec r;
+            r.xy = (uint32_t)x | ((uint32_t)y << 16);
+            r.depth = dep;
+            r.var = v[x];
+            r.ikf = img[x];
+            out[running + wbase + rank_in_warp] = r;
+        }
+        running += total;
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// launch wrappers
+// ------------------------------------------------------------------------------------------------------------------
+int launch_pyramid(cudaStream_t st, uint8_t* img_pool, int64_t img_slot_stride, const int* d_slots, int n, const Geometry& geo) {
+    int launches = 0;
+    for (int l = 1; l < kLevels; ++l) {
+        dim3 grid((geo.pyr_w[l] + PD_TX - 1) / PD_TX, (geo.pyr_h[l] + PD_TY - 1) / PD_TY, n);
+        pyrdown_u8_kernel<<<grid, dim3(PD_TX, PD_TY), 0, st>>>(img_pool, img_slot_stride, d_slots, geo.img_off[l - 1],
+                                                               geo.pyr_w[l - 1], geo.pyr_h[l - 1], geo.img_off[l],
+                                                               geo.pyr_w[l], geo.pyr_h[l]);
+        ++launches;
+    }
+    return launches;
+}
+
+int launch_pack_tex(cudaStream_t st, const uint8_t* img_pool, int64_t img_slot_stride, uint32_t* tex_pool,
+                    int64_t tex_slot_stride, const int* d_slots, int n, const Geometry& geo) {
+    dim3 grid((unsigned)((geo.win_off[kLevels] + 255) / 256), n);
+    pack_tex_kernel<<<grid, 256, 0, st>>>(img_pool, img_slot_stride, tex_pool, tex_slot_stride, d_slots, geo);
+    return 1;
+}
+
+int launch_select(cudaStream_t st, const float* depth_pool, const float* var_pool, int64_t win_slot_stride,
+                  const uint8_t* img_pool, int64_t img_slot_stride, uint8_t* mask_pool, int* rowcount_pool,
+                  int* rowoff_pool, int* count_pool, SelRec* rec_pool, const int* d_slots, int n, const Geometry& geo) {
+    int rows_total = 0;
+    for (int l = 0; l < kLevels; ++l) rows_total += geo.rows[l];
+    select_count_kernel<<<dim3(rows_total, n), SEL_T, 0, st>>>(depth_pool, win_slot_stride, mask_pool, rowcount_pool,
+                                                                rows_total, d_slots, geo);
+    select_scan_kernel<<<dim3(kLevels, n), 1024, 0, st>>>(rowcount_pool, rowoff_pool, count_pool, rows_total, d_slots, geo);
+    select_write_kernel<<<dim3(rows_total, n), SEL_T, 0, st>>>(depth_pool, var_pool, win_slot_stride, img_pool,
+                                                                img_slot_stride, rowoff_pool, rows_total, rec_pool,
+                                                                d_slots, geo);
+    return 3;
+}
+
+}  // namespace ellc

@@ -1,0 +1,193 @@
+/*
+ * ellc_gn.h -- C-ABI of the B200-native photometric Gauss-Newton frame-to-keyframe tracker.
+ *
+ * Drop-in boundary for ELLC's FLAG_DO_PARALLEL_POSE_ESTIMATION path.  The reference has no FFI of its own; the
+ * seam is the C++ call surface of GetImagePoseEstimate / PixelWisePyramid / frame.  Every entry
+ * point below names the reference interface it replaces (paths relative to the reference repo root).  Plain
+ * pointers and sizes only -- no C++ or torch types cross this boundary.  The C++ shim that keeps the reference's
+ * class names on top of this ABI is egomotion_with_local_loop_closures_b200/host/; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - pose: Lie-algebra 6-vector [wx wy wz vx vy vz]; exp(hat(pose)) maps keyframe-camera points to current-camera
+ *     points (src/PixelWisePyramid.cpp:153).
+ *   - images: u8, row-major, contiguous (stride == width).  depth: f32, 0 = no depth (src/Frame.cpp:298).
+ *     variance: f32, -1 = invalid (src/DepthPropagation.cpp:1296).  Level l arrays are (width>>l) x (height>>l).
+ *   - all functions return 0 (ELLC_OK) or a negative ellc_status; none throws or aborts.  Degenerate inputs behave
+ *     like the reference (singular normal equations => zero step, src/PixelWisePyramid.cpp:451).
+ *   - a handle owns one CUDA stream and all device memory; calls on one handle are serialised by the caller,
+ *     different handles may be used concurrently from different host threads (main thread + loop-closure thread,
+ *     src/GlobalOptimize.cpp:241).
+ *   - there is NO CPU fallback: every compute entry point fails with ELLC_ERR_CUDA if no sm_100 device is usable.
+ */
+#ifndef ELLC_GN_H_
+#define ELLC_GN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ELLC_LEVELS 4                 /* util::MAX_PYRAMID_LEVEL, src/ExternVariable.h:40 */
+#define ELLC_MAX_TRACE_ITERS 16       /* per level; the reference's largest MAX_ITER is 12 (src/main.cpp:34) */
+
+typedef enum ellc_status {
+    ELLC_OK = 0,
+    ELLC_ERR_INVALID = -1,            /* bad argument (null pointer, slot out of range, unsupported size) */
+    ELLC_ERR_CUDA = -2,               /* CUDA runtime error or no usable device; see ellc_last_error_string */
+    ELLC_ERR_NOT_READY = -3           /* slot used before it was uploaded / prepared */
+} ellc_status;
+
+/* arithmetic mode of the per-pixel kernel */
+#define ELLC_ARITH_FAST   0           /* fp32 with FMA contraction and reciprocal multiplies (default)            */
+#define ELLC_ARITH_STRICT 1           /* the reference's exact fp32/double operation sequence, no contraction      */
+
+/* pair flags */
+#define ELLC_PAIR_DEFAULT        0
+#define ELLC_PAIR_CONST_WEIGHT   1    /* loop-closure pair: inverse-compositional constant-weight variant
+                                         (src/PixelWisePyramid.cpp:561-974, selected at src/ImageFunc.cpp:241-244) */
+#define ELLC_PAIR_SAVE_WEIGHTS   2    /* accumulate last-iteration weights into the keyframe's weight pyramid
+                                         (saveWeights(true), src/ImageFunc.cpp:280-288)                           */
+
+/* Runtime form of the compile-time configuration surface of src/ExternVariable.h and src/main.cpp:34. */
+typedef struct ellc_config {
+    int32_t width, height;            /* util::ORIG_COLS / ORIG_ROWS (level-0 working size), :50-51              */
+    float   fx, fy, cx, cy;           /* util::ORIG_FX / ORIG_FY / ORIG_CX / ORIG_CY, :53-59                     */
+    int32_t max_iter[ELLC_LEVELS];    /* util::MAX_ITER[level], src/main.cpp:34 = {4,7,9,12}                     */
+    float   huber_d;                  /* util::HUBER_D, :149                                                      */
+    float   camera_pixel_noise_2;     /* util::CAMERA_PIXEL_NOISE_2, :148                                         */
+    float   weight[6];                /* util::weight[], :76                                                      */
+    float   stop_threshold;           /* 1.0f, src/ImageFunc.cpp:251                                              */
+    int32_t arithmetic;               /* ELLC_ARITH_*                                                             */
+    int32_t jacobian_at_warped;       /* 0: PixelWisePyramid.cpp Jacobian (keyframe pixel/depth);
+                                         1: Pyramid.cpp:99-130 variant (warped pixel, transformed depth)          */
+    int32_t max_keyframes;            /* keyframe slots resident on the device                                    */
+    int32_t max_frames;               /* frame slots resident on the device                                       */
+    int32_t ctas_per_pair;            /* thread-block cluster size per pair: 1,2,4,8; 0 = choose from batch size  */
+    int32_t device;                   /* CUDA device ordinal                                                      */
+} ellc_config;
+
+/* One frame-keyframe pair = one call of GetImagePoseEstimate (src/ImageFunc.h:31). */
+typedef struct ellc_pair {
+    int32_t kf_slot;                  /* prev_frame (keyframe) slot                                               */
+    int32_t frame_slot;               /* current_frame slot                                                       */
+    float   init_pose[6];             /* initial relative pose, i.e. the result of src/ImageFunc.cpp:97-108       */
+    int32_t flags;                    /* ELLC_PAIR_*                                                              */
+} ellc_pair;
+
+/* Fixed-size result record (256 B) -- also the unit of the multi-GPU gather. */
+typedef struct ellc_result {
+    float   pose[6];                  /* returned vector<float> of GetImagePoseEstimate (src/ImageFunc.cpp:311)   */
+    float   H[21];                    /* upper triangle (row-major) of the last evaluated hessian                 */
+    float   b[6];                     /* last evaluated sd_param                                                  */
+    int32_t n_selected[ELLC_LEVELS];  /* prev_frame->no_nonZeroDepthPts per level (src/Frame.cpp:299)             */
+    int32_t n_iters[ELLC_LEVELS];     /* executed GN iterations per level                                         */
+    float   res_first[ELLC_LEVELS];   /* sum w r^2 over selected pixels at the level's first iteration (pose on entry) */
+    float   res_last[ELLC_LEVELS];    /* same at the level's last executed iteration (before its update)         */
+    float   weighted_pose[ELLC_LEVELS]; /* PixelWisePyramid::weightedPose after the level's last update          */
+    int32_t n_oob[ELLC_LEVELS];       /* selected pixels warped fully out of bounds at the last iteration         */
+    int32_t status;                   /* 0 ok; bit0: a singular hessian was met (zero step, as the reference)     */
+    int32_t reserved[6];
+} ellc_result;                        /* 64 x 4 B */
+
+/* Per-iteration trace (parity tests / debugging); layout mirrors the members of class PixelWisePyramid. */
+typedef struct ellc_iter_trace {
+    float   H[36];                    /* PixelWisePyramid::hessian                                                */
+    float   b[6];                     /* sd_param                                                                 */
+    float   delta[6];                 /* deltapose                                                                */
+    float   weighted_pose;            /* weightedPose                                                             */
+    float   pose_after[6];            /* *pose after updatePose()                                                 */
+    float   res_sum;                  /* sum w r^2 at the pose before the update                                  */
+    float   weight_sum;               /* sum w                                                                    */
+    int32_t n_oob;
+    int32_t executed;                 /* 1 if this iteration ran                                                  */
+    int32_t pad[5];
+} ellc_iter_trace;                    /* 64 x 4 B */
+
+typedef struct ellc_handle ellc_handle;
+
+/* ---- lifetime -------------------------------------------------------------------------------------------------- */
+void        ellc_default_config(ellc_config* cfg, int32_t width, int32_t height);   /* ExternVariable.h defaults  */
+int         ellc_create(const ellc_config* cfg, ellc_handle** out);
+int         ellc_destroy(ellc_handle* h);
+const char* ellc_last_error_string(const ellc_handle* h);                           /* h may be NULL (create)     */
+const char* ellc_version(void);
+
+/* ---- keyframes and frames: upload from HOST memory ---------------------------------------------------------------
+ * ellc_upload_frame    replaces frame::frame(VideoCapture) after undistort/resize: constructImagePyramids()
+ *                      (src/Frame.cpp:170-182) and per-level calculateGradient() (src/Frame.cpp:185-285).
+ * ellc_upload_keyframe additionally takes the depth / variance pyramids the depth module hands over
+ *                      (frame::depth_pyramid[l], depthMap::depthvararrptr[l]; src/DepthPropagation.h:65-78) and runs
+ *                      calculateNonZeroDepthPts() (src/Frame.cpp:295-301) for every level.
+ * Both are asynchronous on the handle's stream; host buffers must stay valid until ellc_synchronize or the next
+ * synchronous call (pinned memory recommended). */
+int ellc_upload_frame(ellc_handle* h, int32_t frame_slot, const uint8_t* image);
+int ellc_upload_keyframe(ellc_handle* h, int32_t kf_slot, const uint8_t* image,
+                         const float* const depth[ELLC_LEVELS], const float* const var[ELLC_LEVELS]);
+
+/* ---- device-resident inputs ----------------------------------------------------------------------------------------
+ * Raw device pointers into a slot, for callers that already hold the data on the GPU (cudaMemcpyAsync D2D, another
+ * kernel, ...).  After writing, call ellc_prepare_* for the touched slots.  level_offsets (ELLC_LEVELS+1 entries,
+ * in elements) describe how the depth / var levels are concatenated. */
+int ellc_frame_image_devptr(ellc_handle* h, int32_t frame_slot, uint8_t** image);
+int ellc_keyframe_devptrs(ellc_handle* h, int32_t kf_slot, uint8_t** image, float** depth, float** var,
+                          int64_t level_offsets[ELLC_LEVELS + 1]);
+int ellc_prepare_frames(ellc_handle* h, int32_t n, const int32_t* frame_slots);      /* pyramid + gradients, batched */
+int ellc_prepare_keyframes(ellc_handle* h, int32_t n, const int32_t* kf_slots);      /* pyramid + mask/count/selection */
+
+/* ---- the hot path -------------------------------------------------------------------------------------------------
+ * ellc_track_batch replaces n calls of GetImagePoseEstimate(prev_frame, current_frame, ...) (src/ImageFunc.cpp:49-315)
+ * with FLAG_DO_PARALLEL_POSE_ESTIMATION: coarse-to-fine levels 3..0, per level up to max_iter[level] iterations of
+ * calculatePixelWiseParallel() (src/PixelWisePyramid.cpp:416-455) = per-pixel warp / sample / residual / weight /
+ * Jacobian / 6x6 accumulate, hessian.inv(), updatePose(); early-out when weightedPose < stop_threshold
+ * (src/ImageFunc.cpp:251-252).  No host round trip per iteration.  `pairs` and `results` are HOST arrays; the call
+ * returns after the results have been copied back.  `trace` may be NULL; otherwise it receives
+ * n * ELLC_LEVELS * ELLC_MAX_TRACE_ITERS records indexed [pair][level][iter]. */
+int ellc_track_batch(ellc_handle* h, int32_t n, const ellc_pair* pairs, ellc_result* results, ellc_iter_trace* trace);
+
+/* Same, asynchronous: results stay on the device (pointer valid until the next track call on this handle). */
+int ellc_track_batch_async(ellc_handle* h, int32_t n, const ellc_pair* pairs, const ellc_result** device_results);
+int ellc_synchronize(ellc_handle* h);
+
+/* One evaluation of the normal equations at a given pose and level WITHOUT updating the pose: the body of
+ * calculatePixelWiseParallel() up to src/PixelWisePyramid.cpp:442.  out->delta/pose_after/weighted_pose are left 0.
+ * weight_image (host, (width>>level)*(height>>level) f32, display_weightimg :361) may be NULL. */
+int ellc_gn_evaluate(ellc_handle* h, int32_t kf_slot, int32_t frame_slot, int32_t level, const float pose[6],
+                     ellc_iter_trace* out, float* weight_image);
+
+/* hessian.inv() + updatePose() (src/PixelWisePyramid.cpp:451-491) executed by the device code path. */
+int ellc_solve_update(ellc_handle* h, const float H[36], const float b[6], const float pose_in[6],
+                      float pose_out[6], float delta[6], float* weighted_pose);
+
+/* ---- read-back of intermediate products (parity tests) ------------------------------------------------------------ */
+/* image_pyramid[level] (pyrDown chain) and gradientx/gradienty after updationOnPyrChange(level) (src/Frame.cpp:316-327).
+ * image is (w_l x h_l) with w_l = ceil-halved width (cv::pyrDown), gradients are (width>>level) x (height>>level).
+ * Any output pointer may be NULL. */
+int ellc_read_frame_level(ellc_handle* h, int32_t frame_slot, int32_t level, uint8_t* image, float* gradx, float* grady);
+/* frame::mask (0/255) and no_nonZeroDepthPts after updationOnPyrChange(level) on the keyframe; image as above. */
+int ellc_read_keyframe_level(ellc_handle* h, int32_t kf_slot, int32_t level, uint8_t* image, uint8_t* mask, int32_t* count);
+/* pyramid image dims of a level: *w = ceil-halved width, *h likewise */
+int ellc_level_dims(const ellc_handle* h, int32_t level, int32_t* pyr_w, int32_t* pyr_h, int32_t* cols, int32_t* rows);
+
+/* ---- host-side pose algebra used by the callers of the tracker (6 floats, no device work) ------------------------- */
+/* frame::concatenateRelativePose (src/Frame.cpp:503-530): dest = log(exp(a) exp(b)) */
+void ellc_concat_relative(const float a[6], const float b[6], float dest[6]);
+/* frame::concatenateOriginPose (src/Frame.cpp:534-562): dest = log(exp(a) exp(b)^-1) */
+void ellc_concat_origin(const float a[6], const float b[6], float dest[6]);
+/* exp(hat(pose)) as 4x4 row-major (src/Frame.cpp:443-471 calculateRandT) */
+void ellc_se3_exp(const float pose[6], float T[16]);
+
+/* ---- introspection for bench.py ----------------------------------------------------------------------------------- */
+/* kernels launched by this handle since creation (or since the last reset) */
+int64_t ellc_launch_count(const ellc_handle* h);
+void    ellc_reset_launch_count(ellc_handle* h);
+/* cudaStream_t of the handle, as an opaque pointer (for CUDA-event timing on the launching stream) */
+void*   ellc_stream(ellc_handle* h);
+/* device time of the track kernel(s) of the most recent ellc_track_batch* call, in milliseconds (CUDA events) */
+float   ellc_last_track_kernel_ms(ellc_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ELLC_GN_H_ */

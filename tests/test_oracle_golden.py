@@ -1,0 +1,117 @@
+"""CPU: the oracle against the committed golden vectors (cv2.pyrDown / cv2.invert / scipy expm, logm) and itself."""
+import os
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def lib_vec():
+    return np.load(os.path.join(GOLD, "library_vectors.npz"))
+
+
+def hat(p):
+    return np.array([[0, -p[2], p[1], p[3]], [p[2], 0, -p[0], p[4]], [-p[1], p[0], 0, p[5]], [0, 0, 0, 0]], np.float64)
+
+
+def test_pyrdown_bit_exact_vs_cv2(oracle_mod, lib_vec):
+    for i in range(5):
+        assert np.array_equal(oracle_mod.pyrdown(lib_vec[f"pyr_in_{i}"]), lib_vec[f"pyr_out_{i}"])
+
+
+def test_invert6_vs_cv2(oracle_mod, lib_vec):
+    # cv2 4.13 (SIMD/FMA build) and OpenCV 3.0.0's scalar LUImpl<float> agree to a few ulp of the largest entry
+    for H, Hi in zip(lib_vec["inv_in"], lib_vec["inv_out"]):
+        got, ok = oracle_mod.invert6(H)
+        assert ok == 1
+        assert np.abs(got - Hi).max() <= 2e-6 * np.abs(Hi).max()
+    got, ok = oracle_mod.invert6(np.zeros((6, 6), np.float32))
+    assert ok == 0 and lib_vec["inv_singular_ok"][0] == 0 and np.all(got == 0) and np.all(lib_vec["inv_singular_out"] == 0)
+
+
+def test_se3_exp_vs_scipy(oracle_mod, lib_vec):
+    for p, T in zip(lib_vec["se3_poses"], lib_vec["se3_expm"]):
+        got = oracle_mod.se3_exp(p)
+        assert np.abs(got - T).max() <= 4e-7 * max(1.0, np.abs(T).max())
+        assert np.array_equal(got[3], [0, 0, 0, 1])
+
+
+def test_se3_log_roundtrip_and_concat(oracle_mod, lib_vec):
+    poses = lib_vec["se3_poses"]
+    for p in poses[:18]:
+        back = oracle_mod.se3_log(oracle_mod.se3_exp(p))
+        assert np.abs(back - p).max() <= 2e-6 * max(1.0, np.abs(p).max())
+    a, b = poses[:10], poses[5:15]
+    for x, y, r, o in zip(a, b, lib_vec["concat_rel"], lib_vec["concat_org"]):
+        assert np.abs(oracle_mod.concat_relative(x, y) - r).max() <= 3e-6 * max(1.0, np.abs(r).max())
+        assert np.abs(oracle_mod.concat_origin(x, y) - o).max() <= 3e-6 * max(1.0, np.abs(o).max())
+
+
+def test_gradient_matches_border_rules(oracle_mod):
+    rng = np.random.default_rng(1)
+    img = rng.integers(0, 256, (9, 11), dtype=np.uint8)
+    gx, gy = oracle_mod.gradient(img)
+    f = img.astype(np.float32)
+    assert gx[4, 5] == 0.5 * (f[4, 6] - f[4, 4]) and gy[4, 5] == 0.5 * (f[5, 5] - f[3, 5])
+    assert gx[4, 0] == f[4, 1] - f[4, 0] and gx[4, 10] == f[4, 10] - f[4, 9]          # un-halved one-sided
+    assert gy[0, 5] == f[1, 5] - f[0, 5] and gy[8, 5] == f[8, 5] - f[7, 5]
+    assert gx[0, 0] == f[0, 1] - f[0, 0] and gy[0, 0] == f[1, 0] - f[0, 0]            # corner
+    assert gx[0, 5] == 0.5 * (f[0, 6] - f[0, 4])                                       # top row keeps halved gx
+    from egomotion_with_local_loop_closures_b200 import synth
+    sgx, sgy = synth.image_gradient(img)
+    assert np.array_equal(sgx, gx) and np.array_equal(sgy, gy)
+
+
+def test_sampler_quirks(oracle_mod):
+    """src/Frame.h:181-279: per-tap bounds on mixed floored/unfloored coordinates, OOB tap = 0, -1 iff all four OOB."""
+    img = np.arange(20, dtype=np.uint8).reshape(4, 5) * 10          # W=5, H=4
+    s = lambda x, y, c=1: oracle_mod.interp_u8(img, x, y, c)
+    assert s(1.0, 1.0) == 60.0                                       # integer coords: exact pixel
+    assert s(1.5, 1.0) == 65.0
+    assert s(4.0, 3.0) == 190.0                                      # last pixel is in bounds
+    # x in (W-1, W): floor tap valid, ceil tap (tested on unfloored x) OOB -> contributes 0
+    assert s(4.25, 0.0) == np.float32(0.75) * 40.0
+    # y in (H-1, H): bottom taps OOB
+    assert s(0.0, 3.5) == np.float32(0.5) * 150.0
+    # x in (-1, 0): floor = -1 OOB, unfloored x < 0 OOB -> all four OOB -> -1 (check flag) / 0 (no flag)
+    assert s(-0.5, 1.0) == -1.0 and s(-0.5, 1.0, 0) == 0.0
+    assert s(5.0, 1.0) == -1.0 and s(2.0, 4.0) == -1.0 and s(2.0, -0.25) == -1.0
+    g = np.arange(20, dtype=np.float32).reshape(4, 5)
+    assert oracle_mod.interp_f32(g, 4.25, 0.0) == np.float32(0.75) * 4.0
+    assert oracle_mod.interp_f32(g, -3.0, 1.0) == 0.0                # gradient sampler has no -1 sentinel
+
+
+def test_depth_pyramid_numpy_twin_is_bit_exact(oracle_mod):
+    from egomotion_with_local_loop_closures_b200 import synth
+    rng = np.random.default_rng(3)
+    h, w = 48, 64
+    valid = rng.random((h, w)) < 0.3
+    depth0 = np.where(valid, rng.uniform(0.5, 3, (h, w)), 0).astype(np.float32)
+    var0 = np.where(valid, rng.uniform(0.001, 0.05, (h, w)), -1).astype(np.float32)
+    d, v = synth.build_inv_var_depth(depth0, var0)
+    od, ov = oracle_mod.build_depth_pyramid(np.where(valid, depth0, -1).astype(np.float32), var0)
+    for l in range(1, 4):
+        assert np.array_equal(d[l], od[l]) and np.array_equal(v[l], ov[l])
+        assert np.array_equal(d[l] > 0, ov[l] > 0)
+
+
+def test_oracle_end_to_end_regression(oracle_mod):
+    """The committed trace pins the oracle build (compiler / flags drift would show up here)."""
+    g = np.load(os.path.join(GOLD, "oracle_track_160x120.npz"))
+    from egomotion_with_local_loop_closures_b200 import synth
+    w, h = int(g["width"][0]), int(g["height"][0])
+    k = synth.intrinsics(w, h)
+    cfg = oracle_mod.default_config(w, h, fx=float(k["fx"]), fy=float(k["fy"]), cx=float(k["cx"]), cy=float(k["cy"]))
+    depth = [g[f"depth{l}"] for l in range(4)]; var = [g[f"var{l}"] for l in range(4)]
+    pose, tr = oracle_mod.track(cfg, g["kf_image"], g["cur_image"], depth, var, np.zeros(6, np.float32))
+    assert tr["n_selected"] == list(g["n_selected"]) and tr["n_iters"] == list(g["n_iters"])
+    assert np.array_equal(pose, g["pose"])
+    for l in range(4):
+        assert np.array_equal(np.array([it["res_sum_f64"] for it in tr["levels"][l]]), g[f"res_f64_{l}"])
+    assert np.abs(pose - g["gt"]).max() < 1e-3
+    # threaded bands (boost::thread_group analogue) give identical numerics
+    cfg.use_threads = 1
+    pose_t, _ = oracle_mod.track(cfg, g["kf_image"], g["cur_image"], depth, var, np.zeros(6, np.float32), want_trace=False)
+    assert np.array_equal(pose_t, pose)

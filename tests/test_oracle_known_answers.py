@@ -1,0 +1,74 @@
+"""CPU known-answer tests authored for the path: the reference has no tests of its own."""
+import numpy as np
+
+from egomotion_with_local_loop_closures_b200 import synth
+from tests.helpers import oracle_config
+
+
+def test_identity_pose_on_identical_images(oracle_mod, scene_small):
+    case = scene_small
+    cfg = oracle_config(oracle_mod, case)
+    img = case["kf"]["image"]
+    pose, tr = oracle_mod.track(cfg, img, img, case["kf"]["depth"], case["kf"]["var"], np.zeros(6, np.float32))
+    # (X/Z)*fx + cx reproduces the pixel centre only to fp32 rounding, so the residuals are ~1e-5, not exactly 0
+    assert np.abs(pose).max() < 1e-6
+    assert tr["n_iters"] == [1, 1, 1, 1]
+    for l in range(4):
+        it = tr["levels"][l][0]
+        assert it["res_sum_f64"] < 1e-6 * tr["n_selected"][l] and it["weighted_pose"] < 1.0 and it["n_oob"] <= 8   # border pixels can land at -1e-6
+
+
+def test_recovers_ground_truth_pose(oracle_mod):
+    scene = synth.SynthScene(320, 240)
+    kf = scene.keyframe(idepth_noise=0.0)
+    gt = np.array([0.0, 0.0, 0.0, 0.012, -0.008, 0.004])
+    cur = scene.render(synth.se3_exp(gt))
+    case = dict(width=320, height=240)
+    cfg = oracle_config(oracle_mod, case)
+    pose, tr = oracle_mod.track(cfg, kf["image"], cur, kf["depth"], kf["var"], np.zeros(6, np.float32))
+    assert np.abs(pose - gt).max() < 1e-4
+
+
+def test_all_out_of_bounds_gives_zero_step(oracle_mod, scene_small):
+    case = scene_small
+    cfg = oracle_config(oracle_mod, case)
+    far = np.array([0, 0, 0, 50.0, 0, 0], np.float32)
+    pose, tr = oracle_mod.track(cfg, case["kf"]["image"], case["frames"][0], case["kf"]["depth"], case["kf"]["var"], far)
+    assert tr["n_iters"] == [1, 1, 1, 1]
+    assert np.allclose(pose, far, atol=1e-6)
+    for l in range(4):
+        it = tr["levels"][l][0]
+        assert it["n_oob"] == tr["n_selected"][l] and np.all(it["H"] == 0) and np.all(it["delta"] == 0)
+
+
+def test_no_valid_depth_gives_zero_step(oracle_mod, scene_small):
+    case = scene_small
+    cfg = oracle_config(oracle_mod, case)
+    zd = [np.zeros_like(d) for d in case["kf"]["depth"]]
+    zv = [np.full_like(v, -1) for v in case["kf"]["var"]]
+    pose, tr = oracle_mod.track(cfg, case["kf"]["image"], case["frames"][0], zd, zv, np.zeros(6, np.float32))
+    assert tr["n_selected"] == [0, 0, 0, 0] and tr["n_iters"] == [1, 1, 1, 1] and np.all(pose == 0)
+
+
+def test_early_out_and_iteration_caps(oracle_mod, scene_small):
+    case = scene_small
+    cfg = oracle_config(oracle_mod, case)
+    pose, tr = oracle_mod.track(cfg, case["kf"]["image"], case["frames"][0], case["kf"]["depth"], case["kf"]["var"], np.zeros(6, np.float32))
+    for l in range(4):
+        its = tr["levels"][l]
+        assert 1 <= len(its) <= [4, 7, 9, 12][l]
+        assert all(it["weighted_pose"] >= 1.0 for it in its[:-1])                # only the last may be below threshold
+        if len(its) < [4, 7, 9, 12][l]:
+            assert its[-1]["weighted_pose"] < 1.0
+    assert np.abs(pose - case["gt"][0]).max() < 2e-3
+
+
+def test_pyramid_variant_flag_changes_jacobian_only_slightly_near_identity(oracle_mod, scene_small):
+    """Pyramid.cpp (J at warped pixel / Z') and PixelWisePyramid.cpp (J at keyframe pixel / depth) agree at pose 0
+    up to the summation order and the cv::gemm double accumulator of the matrix form."""
+    case = scene_small
+    kpyr = oracle_mod.image_pyramid(case["kf"]["image"]); cpyr = oracle_mod.image_pyramid(case["frames"][0])
+    a = oracle_mod.gn_evaluate(oracle_config(oracle_mod, case), 1, kpyr[1], cpyr[1], case["kf"]["depth"][1], case["kf"]["var"][1], np.zeros(6, np.float32))
+    b = oracle_mod.gn_evaluate(oracle_config(oracle_mod, case, jacobian_at_warped=1), 1, kpyr[1], cpyr[1], case["kf"]["depth"][1], case["kf"]["var"][1], np.zeros(6, np.float32))
+    assert np.abs(a["H"] - b["H"]).max() <= 1e-3 * np.abs(a["H"]).max()
+    assert np.abs(a["b"] - b["b"]).max() <= 1e-3 * np.abs(a["b"]).max()
