@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py -- frame-keyframe GN tracks/sec at 640x480 (BASELINE.json metric), one process per GPU.
+
+    python bench.py [--gpus N --steps K --warmup W]            # our arm (CUDA path through the C-ABI)
+    python bench.py --impl reference [...]                       # reference arm: the CPU tracker on the host cores
+
+A "step" is one batch of the hot path on one GPU: `frames` new frames (pyramid + gradient texels), `keyframes`
+keyframes (pyramid + mask/count/selection) and `pairs` frame-keyframe tracks (each frame against its own keyframe and
+K-1 local-loop-closure candidates), i.e. BASELINE config 5 / config 3 at 640x480.  Weak scaling: every rank gets the same
+amount of work; ranks shard a global pair list by keyframe affinity and all-gather the 256-byte result records (NCCL).
+
+Timed regions
+  value : inputs resident in HBM (level-0 u8 images, keyframe depth/variance pyramids, pair list on the host);
+          prepare_frames + prepare_keyframes + track_batch (+ result D2H, + NCCL all-gather for N>1).
+  e2e   : the same through the reference-facing C-ABI with HOST (pinned) buffers: H2D of every image and depth/variance
+          pyramid and D2H of the results inside the timed region.
+Inputs (hundreds of MB per step) are larger than the 126 MB L2, so no explicit L2 flush is needed between steps.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from egomotion_with_local_loop_closures_b200 import synth  # noqa: E402
+
+W, H = 640, 480
+METRIC = "frame-keyframe GN tracks/sec at 640x480"
+UNIT = "tracks/s"
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# workload
+# ----------------------------------------------------------------------------------------------------------------
+def _render_job(args):
+    kind, seed_scene, T, seed = args
+    scene = _render_job.scenes.get(seed_scene)
+    if scene is None:
+        scene = _render_job.scenes[seed_scene] = synth.SynthScene(W, H, seed_tex=seed_scene)
+    if kind == "kf":
+        kf = scene.keyframe(T, seed_depth=seed, noise_seed=seed + 1)
+        return kf["image"], kf["depth"], kf["var"]
+    return scene.render(T, noise_seed=seed)
+
+
+_render_job.scenes = {}
+
+
+def build_workload(n_kf, n_frames, pairs_per_frame, seed, workers=None):
+    """Seeded pool of keyframes / frames / pairs for one rank.  Rendering is numpy (untimed setup)."""
+    rng = np.random.default_rng(seed)
+    T_kf = [synth.se3_exp(synth.random_pose(rng, rot=np.deg2rad(2.0), trans=0.04)) for _ in range(n_kf)]
+    primary = np.arange(n_frames) % n_kf
+    T_fr = [synth.se3_exp(synth.random_pose(rng, rot=np.deg2rad(1.0), trans=0.015)) @ T_kf[primary[i]] for i in range(n_frames)]
+    jobs = [("kf", 1234 + seed, T_kf[k], 5678 + 17 * k + seed) for k in range(n_kf)]
+    jobs += [("fr", 1234 + seed, T_fr[i], 91011 + i + 1000 * seed) for i in range(n_frames)]
+    workers = workers or min(os.cpu_count() or 1, 32)
+    if workers > 1:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(workers) as pool:
+            out = pool.map(_render_job, jobs, chunksize=max(1, len(jobs) // (4 * workers)))
+    else:
+        out = [_render_job(j) for j in jobs]
+    kfs, frames = out[:n_kf], out[n_kf:]
+    kf_idx, fr_idx, init = [], [], []
+    for i in range(n_frames):
+        others = [k for k in range(n_kf) if k != primary[i]]
+        cand = [int(primary[i])] + list(rng.choice(others, size=min(pairs_per_frame - 1, len(others)), replace=False))
+        for k in cand:
+            rel = synth.relative_pose(T_fr[i], T_kf[k])
+            # init = pose of the "previous frame" (src/ImageFunc.cpp:106): ground truth perturbed by a small motion
+            init.append(rel + synth.random_pose(rng, rot=np.deg2rad(0.3), trans=0.004))
+            kf_idx.append(k)
+            fr_idx.append(i)
+    perm = rng.permutation(len(kf_idx))
+    return dict(kf_images=[k[0] for k in kfs], kf_depth=[k[1] for k in kfs], kf_var=[k[2] for k in kfs], frames=frames,
+                kf_idx=np.array(kf_idx, np.int32)[perm], fr_idx=np.array(fr_idx, np.int32)[perm],
+                init=np.array(init, np.float32)[perm])
+
+
+def algorithmic_bytes(res):
+    """per GN iteration at level L, B_iter(L) = 2 P_L + 9 N_L; summed over executed iterations of all tracks."""
+    P = np.array([(W >> l) * (H >> l) for l in range(4)], np.float64)
+    it = res["n_iters"].astype(np.float64)
+    n = res["n_selected"].astype(np.float64)
+    return float((it * (2.0 * P[None, :] + 9.0 * n)).sum())
+
+
+def setup_bytes(n_frames, n_kf):
+    """B_setup: keyframe depth read + mask write (5 P_L) and pyramid build (P_{L-1} + P_L) per frame / keyframe."""
+    P = np.array([(W >> l) * (H >> l) for l in range(4)], np.float64)
+    pyr = float(sum(P[l - 1] + P[l] for l in range(1, 4)))
+    return n_frames * pyr + n_kf * (pyr + 5.0 * P.sum())
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """Reference arm: the reference's CPU tracker (the oracle restatement -- the real one cannot be compiled here,
+    DESIGN.md) on all host threads, on a bounded sample of the same workload."""
+    if rank != 0:
+        return
+    import oracle
+    cores = os.cpu_count() or 1
+    n_pairs = max(cores * 24, 48)
+    n_frames = max(8, n_pairs // args.pairs_per_frame)
+    wl = build_workload(min(args.keyframes, 8), n_frames, args.pairs_per_frame, seed=0)
+    n_pairs = min(n_pairs, len(wl["kf_idx"]))
+    k = synth.intrinsics(W, H)
+    cfg = oracle.default_config(W, H, fx=float(k["fx"]), fy=float(k["fy"]), cx=float(k["cx"]), cy=float(k["cy"]))
+    times = []
+    for step in range(args.warmup + args.steps):
+        _, secs = oracle.track_many(cfg, wl["kf_idx"][:n_pairs], wl["fr_idx"][:n_pairs], wl["kf_images"], wl["frames"],
+                                    wl["kf_depth"], wl["kf_var"], wl["init"][:n_pairs], n_workers=cores)
+        if step >= args.warmup:
+            times.append(secs)
+    total = float(sum(times))
+    value = n_pairs * len(times) / total
+    sample = f"{n_pairs} pairs/step of the pair_sweep_640x480 workload, {cores} worker threads (1 pair per thread, bands sequential)"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "pair_sweep_640x480", "width": W, "height": H, "pairs_per_step": n_pairs,
+                       "note": "CPU oracle restatement of the reference tracker (g++ -std=c++11 -O3); omits the reference's per-pixel cv::Mat/cv::String overhead, so it is faster than the real binary"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--keyframes", type=int, default=32, help="keyframes per GPU per step")
+    ap.add_argument("--frames", type=int, default=512, help="frames per GPU per step")
+    ap.add_argument("--pairs-per-frame", type=int, default=9, help="1 sequential + K=8 loop-closure candidates")
+    ap.add_argument("--arith", default="fast", choices=["fast", "strict"])
+    ap.add_argument("--cluster", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    # ---- data first (fork-based rendering must precede CUDA initialisation)
+    t_setup = time.time()
+    wl = build_workload(args.keyframes, args.frames, args.pairs_per_frame, seed=rank)
+    n_pairs = len(wl["kf_idx"])
+
+    import torch
+    import torch.distributed as dist
+    from egomotion_with_local_loop_closures_b200 import capi
+    from egomotion_with_local_loop_closures_b200.sharding import gather_results, shard_pairs_by_keyframe
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    k = synth.intrinsics(W, H)
+    cfg = capi.default_config(W, H, fx=float(k["fx"]), fy=float(k["fy"]), cx=float(k["cx"]), cy=float(k["cy"]),
+                              max_keyframes=args.keyframes, max_frames=args.frames, device=local_rank,
+                              arithmetic=capi.ARITH_STRICT if args.arith == "strict" else capi.ARITH_FAST,
+                              ctas_per_pair=args.cluster)
+    trk = capi.Tracker(cfg)
+    stream = torch.cuda.ExternalStream(trk.stream(), device=torch.device("cuda", local_rank))
+
+    # global pair list = concatenation of all ranks' lists (keyframe ids offset per rank); sharding by keyframe affinity
+    # hands every rank exactly its own keyframes back -- the production path for a mixed list.
+    g_kf = np.concatenate([wl["kf_idx"] + r * args.keyframes for r in range(world)]) if world > 1 else wl["kf_idx"]
+    shards = shard_pairs_by_keyframe(g_kf, world)
+    my_idx = shards[rank]
+    if world > 1:
+        assert len(my_idx) == n_pairs and np.all((g_kf[my_idx] // args.keyframes) == g_kf[my_idx][0] // args.keyframes)
+    n_total = n_pairs * world
+
+    # pinned host copies (e2e uploads) -----------------------------------------------------------------------------
+    def pin(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t, t.numpy()
+    keep = []
+    h_frames, h_kf_img, h_kf_depth, h_kf_var = [], [], [], []
+    for f in wl["frames"]:
+        t, a = pin(f); keep.append(t); h_frames.append(a)
+    for i in range(args.keyframes):
+        t, a = pin(wl["kf_images"][i]); keep.append(t); h_kf_img.append(a)
+        d, v = [], []
+        for l in range(4):
+            t, a = pin(wl["kf_depth"][i][l]); keep.append(t); d.append(a)
+            t, a = pin(wl["kf_var"][i][l]); keep.append(t); v.append(a)
+        h_kf_depth.append(d); h_kf_var.append(v)
+    h2d_bytes = sum(a.nbytes for a in h_frames) + sum(a.nbytes for a in h_kf_img) + sum(a.nbytes for d in h_kf_depth for a in d) + \
+        sum(a.nbytes for d in h_kf_var for a in d) + n_pairs * capi.PAIR_DTYPE.itemsize
+    d2h_bytes = n_pairs * capi.RESULT_DTYPE.itemsize
+
+    def upload_all():
+        for i in range(args.keyframes):
+            trk.upload_keyframe(i, h_kf_img[i], h_kf_depth[i], h_kf_var[i])
+        for i in range(args.frames):
+            trk.upload_frame(i, h_frames[i])
+
+    pairs = trk.make_pairs(wl["kf_idx"], wl["fr_idx"], wl["init"])
+    fr_slots = np.arange(args.frames, dtype=np.int32)
+    kf_slots = np.arange(args.keyframes, dtype=np.int32)
+
+    upload_all()
+    trk.synchronize()
+    setup_s = time.time() - t_setup
+
+    kernel_ms = []
+
+    def step_resident():
+        trk.prepare_frames(fr_slots)
+        trk.prepare_keyframes(kf_slots)
+        if world > 1:
+            dptr = trk.track_batch_async(pairs)
+            trk.synchronize()
+            rec = torch.empty((n_pairs, 256), dtype=torch.uint8, device="cuda")
+            capi_copy_d2d(rec, dptr, n_pairs * 256)
+            gathered = gather_results(rec, my_idx, n_total)
+            res = gathered[torch.as_tensor(my_idx, device="cuda")].cpu().numpy().view(capi.RESULT_DTYPE).reshape(-1)
+        else:
+            res = trk.track_batch(pairs)
+        kernel_ms.append(trk.last_track_kernel_ms())
+        return res
+
+    def capi_copy_d2d(dst_tensor, src_ptr, nbytes):
+        from cuda import cudart  # cuda-python is in the image
+        err, = cudart.cudaMemcpy(dst_tensor.data_ptr(), src_ptr, nbytes, cudart.cudaMemcpyKind.cudaMemcpyDeviceToDevice)
+        assert int(err) == 0
+
+    def step_e2e():
+        upload_all()
+        return trk.track_batch(pairs)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, sample_clocks=False):
+        res = None
+        for _ in range(warmup):
+            res = fn()
+        barrier()
+        clk = ClockSampler(local_rank) if sample_clocks else None
+        if clk:
+            clk.start()
+        kernel_ms.clear()
+        trk.reset_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            res = fn()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = trk.launch_count()
+        clocks = clk.stop() if clk else None
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, res, launches, clocks
+
+    ms, res, launches, clocks = timed(step_resident, args.steps, args.warmup, sample_clocks=True)
+    k_ms = float(np.mean(kernel_ms))
+    value = n_total * args.steps / (ms * 1e-3)
+    alg = algorithmic_bytes(res)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = alg / (k_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                "kernel": "gn_track_kernel", "kernel_ms_per_launch": k_ms, "algorithmic_bytes_per_launch": alg,
+                "kernel_share_of_step": k_ms / (ms / args.steps),
+                "mean_iters_per_level": [float(x) for x in res["n_iters"].mean(axis=0)],
+                "mean_selected_per_level": [float(x) for x in res["n_selected"].mean(axis=0)]}
+
+    e2e = None
+    if not args.no_e2e:
+        ems, eres, _, _ = timed(step_e2e, args.steps, max(1, args.warmup))
+        e2e = {"value": n_total * args.steps / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes) * world,
+               "d2h_bytes_per_step": int(d2h_bytes) * world, "ms_per_step": ems / args.steps}
+        assert np.array_equal(eres["pose"], res["pose"]), "e2e and resident paths disagree"
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import oracle
+        cores = os.cpu_count() or 1
+        ns = min(n_pairs, max(cores * 4, 16))
+        ocfg = oracle.default_config(W, H, fx=float(k["fx"]), fy=float(k["fy"]), cx=float(k["cx"]), cy=float(k["cy"]))
+        oposes, secs = oracle.track_many(ocfg, wl["kf_idx"][:ns], wl["fr_idx"][:ns], wl["kf_images"], wl["frames"], wl["kf_depth"],
+                                         wl["kf_var"], wl["init"][:ns], n_workers=cores)
+        perr = float(np.abs(oposes - res["pose"][:ns]).max())
+        cpu_baseline = {"value": ns / secs, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"first {ns} pairs of this step's pair list, {cores} worker threads (1 pair per thread); "
+                                  f"max |pose_gpu - pose_cpu| on the sample = {perr:.2e}"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "pair_sweep_640x480", "width": W, "height": H, "keyframes_per_gpu": args.keyframes,
+                           "frames_per_gpu": args.frames, "pairs_per_gpu_per_step": n_pairs, "pairs_per_frame": args.pairs_per_frame,
+                           "arithmetic": args.arith, "parallelism": f"pairs sharded by keyframe affinity x{world}, result all-gather",
+                           "l2": "inputs (%.0f MB per step per GPU) exceed the 126 MB L2; no flush" % (h2d_bytes / 1e6),
+                           "setup_bytes_per_step": setup_bytes(args.frames, args.keyframes) * world, "setup_seconds": setup_s},
+                "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    trk.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

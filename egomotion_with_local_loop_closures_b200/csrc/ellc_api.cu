@@ -6,7 +6,7 @@
 //   keyframes  img : u8   as frames
 //              depth, var : f32 level windows concatenated                             slot stride = geo.win_off[4]
 //              mask : u8  level windows                                                  "
-//              rec  : SelRec[ ] compacted selected pixels, level l starts at win_off[l]  "
+//              sel_geo : SelGeo[ ] + sel_pix : SelPix[ ] compacted selected pixels, level l at win_off[l]
 //              count[4], rowcount / rowoff scratch
 // Uploads only mark slots dirty; the pyramid / texel / selection kernels run batched over all dirty slots right before
 // the next consumer (track, evaluate, read-back) -- a whole batch costs 4 (frames) + 6 (keyframes) launches.
@@ -32,7 +32,7 @@ struct ellc_handle {
     bool ev_valid;
     // pools
     uint8_t* fr_img; uint32_t* fr_tex;
-    uint8_t* kf_img; float* kf_depth; float* kf_var; uint8_t* kf_mask; SelRec* kf_rec;
+    uint8_t* kf_img; float* kf_depth; float* kf_var; uint8_t* kf_mask; SelGeo* kf_geo; SelPix* kf_pix;
     int* kf_count; int* kf_rowcount; int* kf_rowoff;
     std::vector<uint8_t> fr_state, kf_state;          // 0 empty, 1 image present (dirty), 2 prepared
     std::vector<int> fr_dirty, kf_dirty;
@@ -108,7 +108,7 @@ int ellc_destroy(ellc_handle* h) {
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->fr_img); cudaFree(h->fr_tex); cudaFree(h->kf_img); cudaFree(h->kf_depth); cudaFree(h->kf_var);
-    cudaFree(h->kf_mask); cudaFree(h->kf_rec); cudaFree(h->kf_count); cudaFree(h->kf_rowcount); cudaFree(h->kf_rowoff);
+    cudaFree(h->kf_mask); cudaFree(h->kf_geo); cudaFree(h->kf_pix); cudaFree(h->kf_count); cudaFree(h->kf_rowcount); cudaFree(h->kf_rowoff);
     cudaFree(h->d_slots); cudaFree(h->d_pairs); cudaFree(h->d_results); cudaFree(h->d_trace); cudaFree(h->d_small);
     cudaFree(h->d_weight);
     if (h->h_pin) cudaFreeHost(h->h_pin);
@@ -121,7 +121,7 @@ int ellc_destroy(ellc_handle* h) {
 int ellc_create(const ellc_config* cfg, ellc_handle** out) {
     if (!cfg || !out) { g_create_err = "null argument"; return ELLC_ERR_INVALID; }
     *out = nullptr;
-    if (cfg->width < 16 || cfg->height < 16 || cfg->width > 65535 || cfg->height > 65535 || cfg->max_keyframes < 1 ||
+    if (cfg->width < 16 || cfg->height < 16 || cfg->width > 2047 || cfg->height > 2047 || cfg->max_keyframes < 1 ||
         cfg->max_frames < 1) { g_create_err = "unsupported size / slot count"; return ELLC_ERR_INVALID; }
     if (cfg->jacobian_at_warped) { g_create_err = "jacobian_at_warped (Pyramid.cpp variant) is not built yet"; return ELLC_ERR_INVALID; }
     for (int l = 0; l < kLevels; ++l)
@@ -169,7 +169,8 @@ int ellc_create(const ellc_config* cfg, ellc_handle** out) {
     CR_TRY(cudaMalloc(&h->kf_depth, nk * win * sizeof(float)));
     CR_TRY(cudaMalloc(&h->kf_var, nk * win * sizeof(float)));
     CR_TRY(cudaMalloc(&h->kf_mask, nk * win));
-    CR_TRY(cudaMalloc(&h->kf_rec, nk * win * sizeof(SelRec)));
+    CR_TRY(cudaMalloc(&h->kf_geo, nk * win * sizeof(SelGeo)));
+    CR_TRY(cudaMalloc(&h->kf_pix, nk * win * sizeof(SelPix)));
     CR_TRY(cudaMalloc(&h->kf_count, nk * kLevels * sizeof(int)));
     CR_TRY(cudaMalloc(&h->kf_rowcount, nk * h->rows_total * sizeof(int)));
     CR_TRY(cudaMalloc(&h->kf_rowoff, nk * h->rows_total * sizeof(int)));
@@ -247,7 +248,7 @@ static int prepare_keyframes_impl(ellc_handle* h, int n, const int* slots) {
     h->launches += launch_pyramid(h->stream, h->kf_img, h->geo.img_off[kLevels], d_slots, n, h->geo);
     h->launches += launch_select(h->stream, h->kf_depth, h->kf_var, h->geo.win_off[kLevels], h->kf_img,
                                  h->geo.img_off[kLevels], h->kf_mask, h->kf_rowcount, h->kf_rowoff, h->kf_count,
-                                 h->kf_rec, d_slots, n, h->geo);
+                                 h->kf_geo, h->kf_pix, h->K, d_slots, n, h->geo);
     CU_TRY(h, cudaGetLastError());
     for (int i = 0; i < n; ++i) h->kf_state[slots[i]] = 2;
     return ELLC_OK;
@@ -283,7 +284,7 @@ static void fill_params(const ellc_handle* h, TrackParams& p) {
     p.stop_threshold = h->cfg.stop_threshold;
     p.jacobian_at_warped = h->cfg.jacobian_at_warped;
     p.tex_pool = h->fr_tex; p.tex_slot_stride = h->geo.win_off[kLevels];
-    p.rec_pool = h->kf_rec; p.rec_slot_stride = h->geo.win_off[kLevels];
+    p.geo_pool = h->kf_geo; p.pix_pool = h->kf_pix; p.rec_slot_stride = h->geo.win_off[kLevels];
     p.count_pool = h->kf_count;
     p.level_hi = kLevels - 1; p.level_lo = 0;
 }

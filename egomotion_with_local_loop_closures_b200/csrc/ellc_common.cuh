@@ -11,14 +11,22 @@ namespace ellc {
 constexpr int kLevels = ELLC_LEVELS;
 
 // One selected keyframe pixel (mask != 0, src/Frame.cpp:298), produced once per keyframe level by the selection
-// kernels and streamed by every GN iteration as one coalesced 16-byte load.
-struct __align__(16) SelRec {
-    uint32_t xy;        // x | (y << 16)
-    float    depth;     // prev_frame->depth_pyramid[level](y,x)        (src/PixelWisePyramid.cpp:192)
-    float    var;       // currentDepthMap->depthvararrptr[level][idx]  (src/PixelWisePyramid.cpp:348)
-    uint32_t ikf;       // prev_frame->image_pyramid[level](y,x)        (src/PixelWisePyramid.cpp:189), low byte
+// kernels and streamed by every GN iteration as two coalesced loads (16 B + 4 B, structure of arrays).
+//   SelGeo: the back-projected point of src/PixelWisePyramid.cpp:236-238 -- it depends only on the keyframe pixel, its
+//           depth and the intrinsics, so it is evaluated once (with the reference's exact fp32 operation sequence)
+//           instead of in every iteration -- plus the depth variance of :348.
+//   SelPix: x | y << 11 | I_kf << 22   (x, y < 2048; I_kf = prev_frame->image_pyramid[level](y,x), :189)
+struct __align__(16) SelGeo {
+    float wX, wY;       // worldpointX / worldpointY
+    float depth;        // worldpointZ = depth_ptr[x]
+    float var;          // currentDepthMap->depthvararrptr[level][idx]
 };
-static_assert(sizeof(SelRec) == 16, "SelRec must be 16 bytes");
+static_assert(sizeof(SelGeo) == 16, "SelGeo must be 16 bytes");
+typedef uint32_t SelPix;
+__host__ __device__ inline SelPix selpix_pack(int x, int y, int ikf) { return (uint32_t)x | ((uint32_t)y << 11) | ((uint32_t)ikf << 22); }
+__host__ __device__ inline int selpix_x(SelPix p) { return (int)(p & 0x7ffu); }
+__host__ __device__ inline int selpix_y(SelPix p) { return (int)((p >> 11) & 0x7ffu); }
+__host__ __device__ inline int selpix_i(SelPix p) { return (int)(p >> 22); }
 
 // Packed texel of the current frame at one pyramid level: everything one bilinear tap needs in one 32-bit word.
 //   bits  0.. 7  intensity I (unsigned)
@@ -61,7 +69,8 @@ struct TrackParams {
     int jacobian_at_warped;
     // pools
     const uint32_t* tex_pool;  int64_t tex_slot_stride;       // packed texels, per frame slot
-    const SelRec* rec_pool;    int64_t rec_slot_stride;       // selection records, per keyframe slot
+    const SelGeo* geo_pool;    int64_t rec_slot_stride;       // selection records, per keyframe slot
+    const SelPix* pix_pool;
     const int* count_pool;                                    // [kf_slot][kLevels]
     // work
     const ellc_pair* pairs;

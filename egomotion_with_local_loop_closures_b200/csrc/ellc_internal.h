@@ -11,7 +11,8 @@ int launch_pack_tex(cudaStream_t st, const uint8_t* img_pool, int64_t img_slot_s
                     int64_t tex_slot_stride, const int* d_slots, int n, const Geometry& geo);
 int launch_select(cudaStream_t st, const float* depth_pool, const float* var_pool, int64_t win_slot_stride,
                   const uint8_t* img_pool, int64_t img_slot_stride, uint8_t* mask_pool, int* rowcount_pool,
-                  int* rowoff_pool, int* count_pool, SelRec* rec_pool, const int* d_slots, int n, const Geometry& geo);
+                  int* rowoff_pool, int* count_pool, SelGeo* geo_pool, SelPix* pix_pool, const LevelK* K,
+                  const int* d_slots, int n, const Geometry& geo);
 
 // ellc_track.cu
 // Launches the GN tracking kernel for p.n_pairs pairs with `cluster` CTAs per pair.  Returns kernels launched (1) or a

@@ -1,8 +1,11 @@
 // ellc_lie.cuh -- SE(3) pose algebra and the 6x6 solve, shared by the device kernels and the host-side pose helpers.
 //
 // Replaces (citations relative to the reference repo):
-//   - Eigen .exp() on hat(pose)            src/PixelWisePyramid.cpp:153-159   -> closed-form Rodrigues, evaluated in double
-//   - concatenateRelativePose               src/Frame.cpp:503-530             -> log(exp(a) exp(b)), double, rounded to f32
+//   - Eigen .exp() on hat(pose)            src/PixelWisePyramid.cpp:153-159   -> the same published algorithm Eigen 3.2.5's
+//                                             MatrixExponential<float> implements (Pade 3/5/7 by L1 norm + scaling and
+//                                             squaring, fp32, individually rounded ops), so R|t carry the reference's rounding
+//   - concatenateRelativePose               src/Frame.cpp:503-530             -> log(exp(a) exp(b)): fp32 Pade exps, fp32 4x4
+//                                             product, exact SE(3) logarithm evaluated in double and rounded to fp32
 //   - concatenateOriginPose                 src/Frame.cpp:534-562             -> log(exp(a) exp(b)^-1)
 //   - cv::Mat::inv() (DECOMP_LU, CV_32F)    src/PixelWisePyramid.cpp:451      -> same partial-pivot LU in fp32, eps 10*FLT_EPSILON,
 //                                                                               singular => all-zero inverse (zero step)
@@ -30,41 +33,6 @@ namespace ellc {
 #define ELLC_DADD(a, b) ((a) + (b))
 #endif
 
-// exp(hat(p)) -> R (row-major 3x3) and t, in double.
-__host__ __device__ inline void se3_exp_d(const double p[6], double R[9], double t[3]) {
-    const double wx = p[0], wy = p[1], wz = p[2];
-    const double th2 = wx * wx + wy * wy + wz * wz;
-    double A, B, C;
-    if (th2 < 1e-12) {
-        A = 1.0 - th2 / 6.0;
-        B = 0.5 - th2 / 24.0;
-        C = 1.0 / 6.0 - th2 / 120.0;
-    } else {
-        const double th = sqrt(th2);
-        double s, c;
-#ifdef __CUDA_ARCH__
-        sincos(th, &s, &c);
-#else
-        s = sin(th); c = cos(th);
-#endif
-        A = s / th;
-        B = (1.0 - c) / th2;
-        C = (th - s) / (th2 * th);
-    }
-    // W = hat3(w), W2 = W*W
-    const double W[9] = {0, -wz, wy, wz, 0, -wx, -wy, wx, 0};
-    const double W2[9] = {-(wy * wy + wz * wz), wx * wy, wx * wz,
-                          wx * wy, -(wx * wx + wz * wz), wy * wz,
-                          wx * wz, wy * wz, -(wx * wx + wy * wy)};
-    double V[9];
-    for (int i = 0; i < 9; ++i) {
-        const double id = (i % 4 == 0) ? 1.0 : 0.0;
-        R[i] = id + A * W[i] + B * W2[i];
-        V[i] = id + B * W[i] + C * W2[i];
-    }
-    for (int i = 0; i < 3; ++i) t[i] = V[i * 3 + 0] * p[3] + V[i * 3 + 1] * p[4] + V[i * 3 + 2] * p[5];
-}
-
 // log of a rigid transform (R row-major, t) -> 6-vector, in double.  Entry extraction as src/Frame.cpp:523-528.
 __host__ __device__ inline void se3_log_d(const double R[9], const double t[3], double out[6]) {
     const double ax = 0.5 * (R[7] - R[5]), ay = 0.5 * (R[2] - R[6]), az = 0.5 * (R[3] - R[1]);   // sin(th) n
@@ -84,51 +52,145 @@ __host__ __device__ inline void se3_log_d(const double R[9], const double t[3], 
     for (int i = 0; i < 3; ++i) out[3 + i] = t[i] - 0.5 * wt[i] + coef * wwt[i];
 }
 
+
+// ---- fp32 4x4 helpers (row-major), every operation individually rounded -------------------------------------------
+__host__ __device__ inline void m4_mul_f(const float* x, const float* y, float* r) {
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            float s = ELLC_MUL(x[i * 4 + 0], y[0 * 4 + j]);
+            for (int k = 1; k < 4; ++k) s = ELLC_ADD(s, ELLC_MUL(x[i * 4 + k], y[k * 4 + j]));
+            r[i * 4 + j] = s;
+        }
+}
+// r = c2*P + c1*Q + c0*S + ci*I  (null operands skipped), left to right
+__host__ __device__ inline void m4_poly_f(float c2, const float* P, float c1, const float* Q, float c0, const float* S,
+                                          float ci, float* r) {
+    for (int i = 0; i < 16; ++i) {
+        float s = 0.f;
+        bool first = true;
+        if (P) { s = ELLC_MUL(c2, P[i]); first = false; }
+        if (Q) { const float t = ELLC_MUL(c1, Q[i]); s = first ? t : ELLC_ADD(s, t); first = false; }
+        if (S) { const float t = ELLC_MUL(c0, S[i]); s = first ? t : ELLC_ADD(s, t); first = false; }
+        const float id = (i % 5 == 0) ? ci : 0.f;
+        r[i] = first ? id : ELLC_ADD(s, id);
+    }
+}
+// Solve A X = B for 4x4 fp32 with partial-pivot LU (the PartialPivLU::solve step of the Pade quotient).
+__host__ __device__ inline void lu4_solve_f(const float* Ain, const float* Bin, float* X) {
+    const int n = 4;
+    float A[16], B[16];
+    for (int i = 0; i < 16; ++i) { A[i] = Ain[i]; B[i] = Bin[i]; }
+    for (int i = 0; i < n; ++i) {
+        int p = i;
+        for (int r = i + 1; r < n; ++r)
+            if (fabsf(A[r * n + i]) > fabsf(A[p * n + i])) p = r;
+        if (p != i)
+            for (int c = 0; c < n; ++c) {
+                float t = A[i * n + c]; A[i * n + c] = A[p * n + c]; A[p * n + c] = t;
+                t = B[i * n + c]; B[i * n + c] = B[p * n + c]; B[p * n + c] = t;
+            }
+        const float piv = A[i * n + i];
+        for (int r = i + 1; r < n; ++r) {
+            const float f = ELLC_DIV(A[r * n + i], piv);
+            A[r * n + i] = f;
+            for (int c = i + 1; c < n; ++c) A[r * n + c] = ELLC_SUB(A[r * n + c], ELLC_MUL(f, A[i * n + c]));
+            for (int c = 0; c < n; ++c) B[r * n + c] = ELLC_SUB(B[r * n + c], ELLC_MUL(f, B[i * n + c]));
+        }
+    }
+    for (int c = 0; c < n; ++c)
+        for (int i = n - 1; i >= 0; --i) {
+            float s = B[i * n + c];
+            for (int k = i + 1; k < n; ++k) s = ELLC_SUB(s, ELLC_MUL(A[i * n + k], X[k * n + c]));
+            X[i * n + c] = ELLC_DIV(s, A[i * n + i]);
+        }
+}
+
+// exp(hat(pose)) as a 4x4 fp32 matrix: Pade approximant chosen on the L1 norm (fp32 thresholds 0.42587 / 1.88015,
+// scaling by 2^s above 3.92572), R = (V-U)^-1 (V+U), squared s times.
+__host__ __device__ inline void se3_exp_pade_f(const float p[6], float T[16]) {
+    float M[16];
+    for (int i = 0; i < 16; ++i) M[i] = 0.f;
+    M[1] = -p[2]; M[2] = p[1];  M[3] = p[3];
+    M[4] = p[2];  M[6] = -p[0]; M[7] = p[4];
+    M[8] = -p[1]; M[9] = p[0];  M[11] = p[5];
+    float l1 = 0.f;
+    for (int j = 0; j < 4; ++j) {
+        float s = 0.f;
+        for (int i = 0; i < 4; ++i) s = ELLC_ADD(s, fabsf(M[i * 4 + j]));
+        l1 = fmaxf(l1, s);
+    }
+    float U[16], V[16], A2[16], tmp[16];
+    int squarings = 0;
+    if (l1 < 4.258730016922831e-001f) {
+        m4_mul_f(M, M, A2);
+        m4_poly_f(1.f, A2, 0.f, nullptr, 0.f, nullptr, 60.f, tmp);
+        m4_mul_f(M, tmp, U);
+        m4_poly_f(12.f, A2, 0.f, nullptr, 0.f, nullptr, 120.f, V);
+    } else if (l1 < 1.880152677804762e+000f) {
+        float A4[16];
+        m4_mul_f(M, M, A2);
+        m4_mul_f(A2, A2, A4);
+        m4_poly_f(1.f, A4, 420.f, A2, 0.f, nullptr, 15120.f, tmp);
+        m4_mul_f(M, tmp, U);
+        m4_poly_f(30.f, A4, 3360.f, A2, 0.f, nullptr, 30240.f, V);
+    } else {
+        float A[16], A4[16], A6[16];
+        (void)frexpf(ELLC_DIV(l1, 3.925724783138660f), &squarings);
+        if (squarings < 0) squarings = 0;
+        const float sc = ldexpf(1.0f, squarings);
+        for (int i = 0; i < 16; ++i) A[i] = ELLC_DIV(M[i], sc);
+        m4_mul_f(A, A, A2);
+        m4_mul_f(A2, A2, A4);
+        m4_mul_f(A4, A2, A6);
+        m4_poly_f(1.f, A6, 1512.f, A4, 277200.f, A2, 8648640.f, tmp);
+        m4_mul_f(A, tmp, U);
+        m4_poly_f(56.f, A6, 25200.f, A4, 1995840.f, A2, 17297280.f, V);
+    }
+    float num[16], den[16];
+    for (int i = 0; i < 16; ++i) { num[i] = ELLC_ADD(U[i], V[i]); den[i] = ELLC_ADD(-U[i], V[i]); }
+    lu4_solve_f(den, num, T);
+    for (int s = 0; s < squarings; ++s) {
+        m4_mul_f(T, T, tmp);
+        for (int i = 0; i < 16; ++i) T[i] = tmp[i];
+    }
+}
+
+// log of the rigid part of a 4x4 fp32 matrix -> fp32 6-vector (double evaluation, rounded once)
+__host__ __device__ inline void m4_log_f(const float T[16], float out[6]) {
+    double R[9], t[3], o[6];
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) R[i * 3 + j] = (double)T[i * 4 + j];
+        t[i] = (double)T[i * 4 + 3];
+    }
+    se3_log_d(R, t, o);
+    for (int i = 0; i < 6; ++i) out[i] = (float)o[i];
+}
+
 // dest = log(exp(a) exp(b))   -- frame::concatenateRelativePose, src/Frame.cpp:503-530
 __host__ __device__ inline void concat_relative_f(const float a[6], const float b[6], float dest[6]) {
-    double pa[6], pb[6], Ra[9], ta[3], Rb[9], tb[3], R[9], t[3], o[6];
-    for (int i = 0; i < 6; ++i) { pa[i] = a[i]; pb[i] = b[i]; }
-    se3_exp_d(pa, Ra, ta);
-    se3_exp_d(pb, Rb, tb);
-    for (int i = 0; i < 3; ++i) {
-        for (int j = 0; j < 3; ++j) R[i * 3 + j] = Ra[i * 3 + 0] * Rb[0 * 3 + j] + Ra[i * 3 + 1] * Rb[1 * 3 + j] + Ra[i * 3 + 2] * Rb[2 * 3 + j];
-        t[i] = Ra[i * 3 + 0] * tb[0] + Ra[i * 3 + 1] * tb[1] + Ra[i * 3 + 2] * tb[2] + ta[i];
-    }
-    se3_log_d(R, t, o);
-    for (int i = 0; i < 6; ++i) dest[i] = (float)o[i];
+    float Ta[16], Tb[16], T[16];
+    se3_exp_pade_f(a, Ta);
+    se3_exp_pade_f(b, Tb);
+    m4_mul_f(Ta, Tb, T);
+    m4_log_f(T, dest);
 }
 
-// dest = log(exp(a) exp(b)^-1) -- frame::concatenateOriginPose, src/Frame.cpp:534-562
+// dest = log(exp(a) exp(b)^-1) -- frame::concatenateOriginPose, src/Frame.cpp:534-562 (.inverse() = LU solve against I)
 __host__ __device__ inline void concat_origin_f(const float a[6], const float b[6], float dest[6]) {
-    double pa[6], pb[6], Ra[9], ta[3], Rb[9], tb[3], R[9], t[3], o[6];
-    for (int i = 0; i < 6; ++i) { pa[i] = a[i]; pb[i] = b[i]; }
-    se3_exp_d(pa, Ra, ta);
-    se3_exp_d(pb, Rb, tb);
-    // inv(Tb) = [Rb^T, -Rb^T tb]
-    double Ri[9], ti[3];
-    for (int i = 0; i < 3; ++i) {
-        for (int j = 0; j < 3; ++j) Ri[i * 3 + j] = Rb[j * 3 + i];
-    }
-    for (int i = 0; i < 3; ++i) ti[i] = -(Ri[i * 3 + 0] * tb[0] + Ri[i * 3 + 1] * tb[1] + Ri[i * 3 + 2] * tb[2]);
-    for (int i = 0; i < 3; ++i) {
-        for (int j = 0; j < 3; ++j) R[i * 3 + j] = Ra[i * 3 + 0] * Ri[0 * 3 + j] + Ra[i * 3 + 1] * Ri[1 * 3 + j] + Ra[i * 3 + 2] * Ri[2 * 3 + j];
-        t[i] = Ra[i * 3 + 0] * ti[0] + Ra[i * 3 + 1] * ti[1] + Ra[i * 3 + 2] * ti[2] + ta[i];
-    }
-    se3_log_d(R, t, o);
-    for (int i = 0; i < 6; ++i) dest[i] = (float)o[i];
+    float Ta[16], Tb[16], Ti[16], T[16], I[16];
+    se3_exp_pade_f(a, Ta);
+    se3_exp_pade_f(b, Tb);
+    for (int i = 0; i < 16; ++i) I[i] = (i % 5 == 0) ? 1.f : 0.f;
+    lu4_solve_f(Tb, I, Ti);
+    m4_mul_f(Ta, Ti, T);
+    m4_log_f(T, dest);
 }
 
-// exp(hat(pose)) rounded to fp32: SE3_vec[12] = r11 r12 r13 t1 r21 ... (src/PixelWisePyramid.cpp:162-173)
+// exp(hat(pose)): SE3_vec[12] = r11 r12 r13 t1 r21 ... (src/PixelWisePyramid.cpp:162-173)
 __host__ __device__ inline void pose_to_rt_f(const float pose[6], float Rt[12]) {
-    double p[6], R[9], t[3];
-    for (int i = 0; i < 6; ++i) p[i] = pose[i];
-    se3_exp_d(p, R, t);
-    for (int i = 0; i < 3; ++i) {
-        Rt[i * 4 + 0] = (float)R[i * 3 + 0];
-        Rt[i * 4 + 1] = (float)R[i * 3 + 1];
-        Rt[i * 4 + 2] = (float)R[i * 3 + 2];
-        Rt[i * 4 + 3] = (float)t[i];
-    }
+    float T[16];
+    se3_exp_pade_f(pose, T);
+    for (int i = 0; i < 12; ++i) Rt[i] = T[i];
 }
 
 // cv::Mat::inv() for a 6x6 CV_32F: partial-pivot LU on [A | I] in fp32 (each op individually rounded, as OpenCV's

@@ -5,7 +5,7 @@
 //                           intensity into one 32-bit texel per pixel (ellc_common.cuh) so that a bilinear tap of the GN
 //                           kernel is a single gather
 //   K3  select_*_kernel     frame::calculateNonZeroDepthPts: mask = depth > 0, count (src/Frame.cpp:295-301), plus an
-//                           order-preserving compaction of the selected pixels into SelRec lists (raster order)
+//                           order-preserving compaction of the selected pixels into SelGeo/SelPix lists (raster order)
 //
 // All kernels are batched over slots (blockIdx.z / blockIdx.y) so that a whole batch of frames costs 4 launches.
 #include "ellc_internal.h"
@@ -88,7 +88,7 @@ pack_tex_kernel(const uint8_t* __restrict__ img_pool, int64_t img_slot_stride, u
 
 // ------------------------------------------------------------------------------------------------------------------
 // K3: selection.  Pass A counts per row and writes the mask, pass B scans the row counts per level, pass C writes the
-// compacted SelRec lists in raster order (deterministic).
+// compacted SelGeo/SelPix lists in raster order (deterministic).
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int SEL_T = 128;
 
@@ -176,20 +176,27 @@ select_scan_kernel(const int* __restrict__ rowcount_pool, int* __restrict__ rowo
     if (threadIdx.x == 0) count_pool[slot * kLevels + level] = s_carry;
 }
 
+struct KSet { LevelK k[kLevels]; };
+
 __global__ void __launch_bounds__(SEL_T)
 select_write_kernel(const float* __restrict__ depth_pool, const float* __restrict__ var_pool, int64_t win_slot_stride,
                     const uint8_t* __restrict__ img_pool, int64_t img_slot_stride, const int* __restrict__ rowoff_pool,
-                    int rows_total, SelRec* __restrict__ rec_pool, const int* __restrict__ slots, Geometry geo) {
+                    int rows_total, SelGeo* __restrict__ geo_pool, SelPix* __restrict__ pix_pool, KSet ks,
+                    const int* __restrict__ slots, Geometry geo) {
     int level, y;
     row_to_level(geo, blockIdx.x, level, y);
     const int slot = slots[blockIdx.y];
     const int cols = geo.cols[level];
+    const LevelK K = ks.k[level];
     const int64_t off = (int64_t)slot * win_slot_stride + geo.win_off[level] + (int64_t)y * cols;
     const float* __restrict__ d = depth_pool + off;
     const float* __restrict__ v = var_pool + off;
     const uint8_t* __restrict__ img = img_pool + (int64_t)slot * img_slot_stride + geo.img_off[level] + (int64_t)y * geo.pyr_w[level];
-    SelRec* __restrict__ out = rec_pool + (int64_t)slot * win_slot_stride + geo.win_off[level] +
-                               rowoff_pool[(int64_t)slot * rows_total + blockIdx.x];
+    const int64_t obase = (int64_t)slot * win_slot_stride + geo.win_off[level] + rowoff_pool[(int64_t)slot * rows_total + blockIdx.x];
+    SelGeo* __restrict__ og = geo_pool + obase;
+    SelPix* __restrict__ op = pix_pool + obase;
+    // worldpointY's numerator factor (y - cy) is row-constant
+    const float yc = __fsub_rn((float)y, K.cy);
     __shared__ int s_w[SEL_T / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int running = 0;
@@ -210,12 +217,15 @@ select_write_kernel(const float* __restrict__ depth_pool, const float* __restric
             total += c;
         }
         if (sel) {
-            SelRec r;
-            r.xy = (uint32_t)x | ((uint32_t)y << 16);
-            r.depth = dep;
-            r.var = v[x];
-            r.ikf = img[x];
-            out[running + wbase + rank_in_warp] = r;
+            SelGeo g;
+            // src/PixelWisePyramid.cpp:236-237: (x - cx) * depth / fx, each operation rounded to fp32
+            g.wX = __fdiv_rn(__fmul_rn(__fsub_rn((float)x, K.cx), dep), K.fx);
+            g.wY = __fdiv_rn(__fmul_rn(yc, dep), K.fy);
+            g.depth = dep;
+            g.var = v[x];
+            const int o = running + wbase + rank_in_warp;
+            og[o] = g;
+            op[o] = selpix_pack(x, y, img[x]);
         }
         running += total;
         __syncthreads();
@@ -246,15 +256,18 @@ int launch_pack_tex(cudaStream_t st, const uint8_t* img_pool, int64_t img_slot_s
 
 int launch_select(cudaStream_t st, const float* depth_pool, const float* var_pool, int64_t win_slot_stride,
                   const uint8_t* img_pool, int64_t img_slot_stride, uint8_t* mask_pool, int* rowcount_pool,
-                  int* rowoff_pool, int* count_pool, SelRec* rec_pool, const int* d_slots, int n, const Geometry& geo) {
+                  int* rowoff_pool, int* count_pool, SelGeo* geo_pool, SelPix* pix_pool, const LevelK* K,
+                  const int* d_slots, int n, const Geometry& geo) {
     int rows_total = 0;
     for (int l = 0; l < kLevels; ++l) rows_total += geo.rows[l];
     select_count_kernel<<<dim3(rows_total, n), SEL_T, 0, st>>>(depth_pool, win_slot_stride, mask_pool, rowcount_pool,
                                                                 rows_total, d_slots, geo);
     select_scan_kernel<<<dim3(kLevels, n), 1024, 0, st>>>(rowcount_pool, rowoff_pool, count_pool, rows_total, d_slots, geo);
+    KSet ks;
+    for (int l = 0; l < kLevels; ++l) ks.k[l] = K[l];
     select_write_kernel<<<dim3(rows_total, n), SEL_T, 0, st>>>(depth_pool, var_pool, win_slot_stride, img_pool,
-                                                                img_slot_stride, rowoff_pool, rows_total, rec_pool,
-                                                                d_slots, geo);
+                                                                img_slot_stride, rowoff_pool, rows_total, geo_pool,
+                                                                pix_pool, ks, d_slots, geo);
     return 3;
 }
 

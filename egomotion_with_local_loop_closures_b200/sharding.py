@@ -1,0 +1,64 @@
+"""Multi-GPU plumbing: shard independent frame-keyframe pairs across ranks and gather the fixed-size result records.
+
+The path has no data-path collective: a track reads only its own pair.  Pairs are partitioned by
+keyframe affinity -- every pair of a keyframe goes to the same rank, so its pyramid / selection lists are built
+once -- with keyframes dealt to the least-loaded rank (by pair count).  The only exchange is one all-gather of
+256-byte ellc_result records at the end of a batch (NCCL over NVLink on GPUs, gloo in the CPU tests).
+"""
+import numpy as np
+
+
+def shard_pairs_by_keyframe(kf_ids, world_size):
+    """Return a list (one entry per rank) of index arrays into the pair list.
+
+    Deterministic: keyframes are visited by decreasing pair count (ties by id) and given to the rank with the fewest
+    pairs so far (ties by rank).  Within a rank, pairs keep their original order."""
+    kf_ids = np.asarray(kf_ids)
+    uniq, counts = np.unique(kf_ids, return_counts=True)
+    order = np.lexsort((uniq, -counts))
+    load = np.zeros(world_size, np.int64)
+    owner = {}
+    for i in order:
+        r = int(np.lexsort((np.arange(world_size), load))[0])
+        owner[int(uniq[i])] = r
+        load[r] += counts[i]
+    ranks = np.array([owner[int(k)] for k in kf_ids], np.int64) if len(kf_ids) else np.zeros(0, np.int64)
+    return [np.nonzero(ranks == r)[0] for r in range(world_size)]
+
+
+def gather_results(local_records, local_indices, n_total, group=None, device=None):
+    """All-gather variable-length shards of fixed-size records and restore the global pair order.
+
+    local_records: (n_local, record_bytes) uint8 torch tensor (CUDA for NCCL, CPU for gloo) or numpy structured array.
+    local_indices: global pair indices of the local records.  Returns a (n_total, record_bytes) uint8 tensor on every rank.
+    """
+    import torch
+    import torch.distributed as dist
+
+    if isinstance(local_records, np.ndarray):
+        local_records = torch.from_numpy(local_records.view(np.uint8).reshape(len(local_records), -1))
+    if device is not None:
+        local_records = local_records.to(device)
+    dev = local_records.device
+    rec_bytes = local_records.shape[1] if local_records.ndim == 2 else 256
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    idx = torch.as_tensor(np.asarray(local_indices, np.int64), device=dev)
+    out = torch.zeros((n_total, rec_bytes), dtype=torch.uint8, device=dev)
+    if world == 1:
+        out[idx] = local_records
+        return out
+    n_local = torch.tensor([local_records.shape[0]], dtype=torch.int64, device=dev)
+    counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(counts, n_local, group=group)
+    cmax = int(max(int(c.item()) for c in counts))
+    pad_rec = torch.zeros((cmax, rec_bytes), dtype=torch.uint8, device=dev)
+    pad_idx = torch.full((cmax,), -1, dtype=torch.int64, device=dev)
+    pad_rec[: local_records.shape[0]] = local_records
+    pad_idx[: idx.shape[0]] = idx
+    all_rec = torch.empty((world * cmax, rec_bytes), dtype=torch.uint8, device=dev)
+    all_idx = torch.empty((world * cmax,), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(all_rec, pad_rec, group=group)
+    dist.all_gather_into_tensor(all_idx, pad_idx, group=group)
+    keep = all_idx >= 0
+    out[all_idx[keep]] = all_rec[keep]
+    return out

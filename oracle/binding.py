@@ -33,7 +33,8 @@ class Config(C.Structure):
 class Iter(C.Structure):
     _fields_ = [("H", C.c_float * 36), ("b", C.c_float * 6), ("delta", C.c_float * 6),
                 ("weighted_pose", C.c_float), ("pose_after", C.c_float * 6),
-                ("res_sum_f32", C.c_float), ("res_sum_f64", C.c_double), ("n_oob", C.c_int)]
+                ("res_sum_f32", C.c_float), ("res_sum_f64", C.c_double), ("n_oob", C.c_int), ("pad_", C.c_int),
+                ("H_f64", C.c_double * 36), ("b_f64", C.c_double * 6)]
 
 
 class Trace(C.Structure):
@@ -193,7 +194,8 @@ def iter_to_dict(it):
     return dict(H=np.array(it.H, np.float32).reshape(6, 6), b=np.array(it.b, np.float32),
                 delta=np.array(it.delta, np.float32), weighted_pose=it.weighted_pose,
                 pose_after=np.array(it.pose_after, np.float32), res_sum_f32=it.res_sum_f32,
-                res_sum_f64=it.res_sum_f64, n_oob=it.n_oob)
+                res_sum_f64=it.res_sum_f64, n_oob=it.n_oob,
+                H_f64=np.array(it.H_f64, np.float64).reshape(6, 6), b_f64=np.array(it.b_f64, np.float64))
 
 
 def gn_evaluate(cfg, level, kf_img, cur_img, depth, var, pose, want_weights=False):

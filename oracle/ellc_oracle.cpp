@@ -212,6 +212,8 @@ struct BandAcc {
     float res_f32;
     double res_f64;
     int n_oob;
+    double Hd[36];       // same fp32 products, double accumulation (diagnostic)
+    double bsum[6];
 };
 
 struct LevelView {
@@ -314,8 +316,9 @@ void pixelwise_band(const ellc_oracle_config* cfg, const Intr& K, const LevelVie
             float wJ[6];
             for (int i = 0; i < 6; ++i) wJ[i] = J[i] * res_weight;
             for (int i = 0; i < 6; ++i)
-                for (int j = 0; j < 6; ++j) acc->H[i * 6 + j] += wJ[i] * J[j];
+                for (int j = 0; j < 6; ++j) { const float pr = wJ[i] * J[j]; acc->H[i * 6 + j] += pr; acc->Hd[i * 6 + j] += (double)pr; }
             const float rw = residual * res_weight;
+            for (int i = 0; i < 6; ++i) acc->bsum[i] += (double)(J[i] * rw);
             if (!at_warped) {
                 for (int i = 0; i < 6; ++i) acc->b[i] += J[i] * rw;
             } else {
@@ -363,7 +366,11 @@ void evaluate_level(const ellc_oracle_config* cfg, int level, const LevelView& l
     out->res_sum_f32 = acc[0].res_f32;
     out->res_sum_f64 = acc[0].res_f64;
     out->n_oob = acc[0].n_oob;
+    for (int i = 0; i < 36; ++i) out->H_f64[i] = acc[0].Hd[i];
+    for (int i = 0; i < 6; ++i) out->b_f64[i] = acc[0].bsum[i];
     for (int t = 1; t < nb; ++t) {
+        for (int i = 0; i < 36; ++i) out->H_f64[i] += acc[t].Hd[i];
+        for (int i = 0; i < 6; ++i) out->b_f64[i] += acc[t].bsum[i];
         for (int i = 0; i < 36; ++i) out->H[i] = out->H[i] + acc[t].H[i];
         for (int i = 0; i < 6; ++i) out->b[i] = out->b[i] + acc[t].b[i];
         out->res_sum_f32 += acc[t].res_f32;
