@@ -79,6 +79,7 @@ static void build_intrinsics(const ellc_config& c, LevelK K[kLevels]) {
         K[l].cx = (float)(c.cx / s); K[l].cy = (float)(c.cy / s);
         K[l].ifx = 1.0f / K[l].fx; K[l].ify = 1.0f / K[l].fy;
         K[l].fy_ifx = K[l].fy / K[l].fx; K[l].fx_ify = K[l].fx / K[l].fy;
+        K[l].cm1 = (float)((c.width >> l) - 1); K[l].rm1 = (float)((c.height >> l) - 1);
     }
 }
 

@@ -56,6 +56,7 @@ struct LevelK {
     float fx, fy, cx, cy;
     float ifx, ify;            // fast-mode reciprocals
     float fy_ifx, fx_ify;      // fy/fx, fx/fy
+    float cm1, rm1;            // float(cols-1), float(rows-1): nCols / nRows of src/Frame.h:196-197
 };
 
 struct TrackParams {

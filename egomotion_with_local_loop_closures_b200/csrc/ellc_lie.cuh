@@ -10,6 +10,10 @@
 //   - cv::Mat::inv() (DECOMP_LU, CV_32F)    src/PixelWisePyramid.cpp:451      -> same partial-pivot LU in fp32, eps 10*FLT_EPSILON,
 //                                                                               singular => all-zero inverse (zero step)
 //   - updatePose()                          src/PixelWisePyramid.cpp:460-491
+//
+// Everything here runs once per GN iteration on ONE thread while the rest of the CTA waits, so it is written to stay in
+// registers: fixed-size arrays, fully unrollable loops, and row swaps done with selects instead of dynamic indexing
+// (the arithmetic and its order are unchanged by that).
 #pragma once
 
 #include <cuda_runtime.h>
@@ -24,6 +28,7 @@ namespace ellc {
 #define ELLC_DIV(a, b) __fdiv_rn((a), (b))
 #define ELLC_DMUL(a, b) __dmul_rn((a), (b))
 #define ELLC_DADD(a, b) __dadd_rn((a), (b))
+#define ELLC_UNROLL _Pragma("unroll")
 #else
 #define ELLC_MUL(a, b) ((a) * (b))
 #define ELLC_ADD(a, b) ((a) + (b))
@@ -31,91 +36,137 @@ namespace ellc {
 #define ELLC_DIV(a, b) ((a) / (b))
 #define ELLC_DMUL(a, b) ((a) * (b))
 #define ELLC_DADD(a, b) ((a) + (b))
+#define ELLC_UNROLL
 #endif
 
-// log of a rigid transform (R row-major, t) -> 6-vector, in double.  Entry extraction as src/Frame.cpp:523-528.
+// log of a rigid transform (R row-major, t) -> 6-vector, in double.  Entry extraction as src/Frame.cpp:523-528:
+// omega = theta/sin(theta) * (antisymmetric part), v = V^-1 t.  For rotations below ~17 degrees (everything this
+// tracker produces) theta/sin(theta) and the V^-1 coefficient come from their power series (no atan2/sin/cos calls);
+// both agree with the closed forms to ~1e-16, far inside the final rounding to fp32.
 __host__ __device__ inline void se3_log_d(const double R[9], const double t[3], double out[6]) {
     const double ax = 0.5 * (R[7] - R[5]), ay = 0.5 * (R[2] - R[6]), az = 0.5 * (R[3] - R[1]);   // sin(th) n
-    const double s = sqrt(ax * ax + ay * ay + az * az);
+    const double s2 = ax * ax + ay * ay + az * az;
     const double c = 0.5 * (R[0] + R[4] + R[8] - 1.0);
-    const double th = atan2(s, c);
-    double k;
-    if (s < 1e-7) k = (c > 0) ? 1.0 + th * th / 6.0 : 0.0;
-    else k = th / s;
+    double k, th2;
+    if (c > 0.5 && s2 < 0.09 * c * c) {
+        // th = atan(q), q = s/c; k = th/s = (atan(q)/q)/c; atan(q)/q = sum (-1)^n q^2n/(2n+1), |q| < 0.3
+        const double q2 = s2 / (c * c);
+        double p = 0.0;
+        ELLC_UNROLL
+        for (int n = 17; n >= 0; --n) p = p * q2 + ((n & 1) ? -1.0 : 1.0) / (double)(2 * n + 1);
+        k = p / c;
+        th2 = p * p * q2;                     // th^2 = (q p)^2
+    } else {
+        const double s = sqrt(s2);
+        const double th = atan2(s, c);
+        if (s < 1e-7) k = (c > 0) ? 1.0 + th * th / 6.0 : 0.0;
+        else k = th / s;
+        th2 = th * th;
+    }
     const double w[3] = {k * ax, k * ay, k * az};
-    double coef;
-    if (th < 1e-4) coef = 1.0 / 12.0 + th * th / 720.0;
-    else coef = (1.0 - (th * sin(th)) / (2.0 * (1.0 - cos(th)))) / (th * th);
+    double coef;                              // (1 - th sin th / (2 (1 - cos th))) / th^2
+    if (th2 < 0.1) {
+        coef = 1.0 / 12.0 + th2 * (1.0 / 720.0 + th2 * (1.0 / 30240.0 + th2 * (1.0 / 1209600.0 + th2 * (1.0 / 47900160.0 +
+               th2 * (691.0 / 1307674368000.0)))));
+    } else {
+        const double th = sqrt(th2);
+        coef = (1.0 - (th * sin(th)) / (2.0 * (1.0 - cos(th)))) / th2;
+    }
     const double wt[3] = {w[1] * t[2] - w[2] * t[1], w[2] * t[0] - w[0] * t[2], w[0] * t[1] - w[1] * t[0]};
     const double wwt[3] = {w[1] * wt[2] - w[2] * wt[1], w[2] * wt[0] - w[0] * wt[2], w[0] * wt[1] - w[1] * wt[0]};
     out[0] = w[0]; out[1] = w[1]; out[2] = w[2];
+    ELLC_UNROLL
     for (int i = 0; i < 3; ++i) out[3 + i] = t[i] - 0.5 * wt[i] + coef * wwt[i];
 }
 
-
 // ---- fp32 4x4 helpers (row-major), every operation individually rounded -------------------------------------------
-__host__ __device__ inline void m4_mul_f(const float* x, const float* y, float* r) {
-    for (int i = 0; i < 4; ++i)
+__host__ __device__ inline void m4_mul_f(const float (&x)[16], const float (&y)[16], float (&r)[16]) {
+    ELLC_UNROLL
+    for (int i = 0; i < 4; ++i) {
+        ELLC_UNROLL
         for (int j = 0; j < 4; ++j) {
             float s = ELLC_MUL(x[i * 4 + 0], y[0 * 4 + j]);
+            ELLC_UNROLL
             for (int k = 1; k < 4; ++k) s = ELLC_ADD(s, ELLC_MUL(x[i * 4 + k], y[k * 4 + j]));
             r[i * 4 + j] = s;
         }
-}
-// r = c2*P + c1*Q + c0*S + ci*I  (null operands skipped), left to right
-__host__ __device__ inline void m4_poly_f(float c2, const float* P, float c1, const float* Q, float c0, const float* S,
-                                          float ci, float* r) {
-    for (int i = 0; i < 16; ++i) {
-        float s = 0.f;
-        bool first = true;
-        if (P) { s = ELLC_MUL(c2, P[i]); first = false; }
-        if (Q) { const float t = ELLC_MUL(c1, Q[i]); s = first ? t : ELLC_ADD(s, t); first = false; }
-        if (S) { const float t = ELLC_MUL(c0, S[i]); s = first ? t : ELLC_ADD(s, t); first = false; }
-        const float id = (i % 5 == 0) ? ci : 0.f;
-        r[i] = first ? id : ELLC_ADD(s, id);
     }
 }
-// Solve A X = B for 4x4 fp32 with partial-pivot LU (the PartialPivLU::solve step of the Pade quotient).
-__host__ __device__ inline void lu4_solve_f(const float* Ain, const float* Bin, float* X) {
-    const int n = 4;
+// r = c2*P + c1*Q + c0*S + ci*I, left to right; NP = number of leading matrix operands used (1..3)
+template <int NP>
+__host__ __device__ inline void m4_poly_f(float c2, const float (&P)[16], float c1, const float (&Q)[16], float c0,
+                                          const float (&S)[16], float ci, float (&r)[16]) {
+    ELLC_UNROLL
+    for (int i = 0; i < 16; ++i) {
+        float s = ELLC_MUL(c2, P[i]);
+        if (NP >= 2) s = ELLC_ADD(s, ELLC_MUL(c1, Q[i]));
+        if (NP >= 3) s = ELLC_ADD(s, ELLC_MUL(c0, S[i]));
+        r[i] = ELLC_ADD(s, (i % 5 == 0) ? ci : 0.f);
+    }
+}
+// Solve A X = B for 4x4 fp32 with partial-pivot LU (the PartialPivLU::solve step of the Pade quotient, and .inverse()).
+__host__ __device__ inline void lu4_solve_f(const float (&Ain)[16], const float (&Bin)[16], float (&X)[16]) {
+    constexpr int n = 4;
     float A[16], B[16];
+    ELLC_UNROLL
     for (int i = 0; i < 16; ++i) { A[i] = Ain[i]; B[i] = Bin[i]; }
+    ELLC_UNROLL
     for (int i = 0; i < n; ++i) {
         int p = i;
-        for (int r = i + 1; r < n; ++r)
-            if (fabsf(A[r * n + i]) > fabsf(A[p * n + i])) p = r;
-        if (p != i)
+        float best = fabsf(A[i * n + i]);
+        ELLC_UNROLL
+        for (int r = i + 1; r < n; ++r) {
+            const float v = fabsf(A[r * n + i]);
+            if (v > best) { best = v; p = r; }
+        }
+        ELLC_UNROLL
+        for (int r = i + 1; r < n; ++r) {                 // swap rows i and p (p is data dependent: select, don't index)
+            const bool sw = (p == r);
+            ELLC_UNROLL
             for (int c = 0; c < n; ++c) {
-                float t = A[i * n + c]; A[i * n + c] = A[p * n + c]; A[p * n + c] = t;
-                t = B[i * n + c]; B[i * n + c] = B[p * n + c]; B[p * n + c] = t;
+                const float a0 = A[i * n + c], a1 = A[r * n + c];
+                A[i * n + c] = sw ? a1 : a0; A[r * n + c] = sw ? a0 : a1;
+                const float b0 = B[i * n + c], b1 = B[r * n + c];
+                B[i * n + c] = sw ? b1 : b0; B[r * n + c] = sw ? b0 : b1;
             }
+        }
         const float piv = A[i * n + i];
+        ELLC_UNROLL
         for (int r = i + 1; r < n; ++r) {
             const float f = ELLC_DIV(A[r * n + i], piv);
             A[r * n + i] = f;
+            ELLC_UNROLL
             for (int c = i + 1; c < n; ++c) A[r * n + c] = ELLC_SUB(A[r * n + c], ELLC_MUL(f, A[i * n + c]));
+            ELLC_UNROLL
             for (int c = 0; c < n; ++c) B[r * n + c] = ELLC_SUB(B[r * n + c], ELLC_MUL(f, B[i * n + c]));
         }
     }
-    for (int c = 0; c < n; ++c)
+    ELLC_UNROLL
+    for (int c = 0; c < n; ++c) {
+        ELLC_UNROLL
         for (int i = n - 1; i >= 0; --i) {
             float s = B[i * n + c];
+            ELLC_UNROLL
             for (int k = i + 1; k < n; ++k) s = ELLC_SUB(s, ELLC_MUL(A[i * n + k], X[k * n + c]));
             X[i * n + c] = ELLC_DIV(s, A[i * n + i]);
         }
+    }
 }
 
 // exp(hat(pose)) as a 4x4 fp32 matrix: Pade approximant chosen on the L1 norm (fp32 thresholds 0.42587 / 1.88015,
 // scaling by 2^s above 3.92572), R = (V-U)^-1 (V+U), squared s times.
-__host__ __device__ inline void se3_exp_pade_f(const float p[6], float T[16]) {
+__host__ __device__ inline void se3_exp_pade_f(const float p[6], float (&T)[16]) {
     float M[16];
+    ELLC_UNROLL
     for (int i = 0; i < 16; ++i) M[i] = 0.f;
     M[1] = -p[2]; M[2] = p[1];  M[3] = p[3];
     M[4] = p[2];  M[6] = -p[0]; M[7] = p[4];
     M[8] = -p[1]; M[9] = p[0];  M[11] = p[5];
     float l1 = 0.f;
+    ELLC_UNROLL
     for (int j = 0; j < 4; ++j) {
         float s = 0.f;
+        ELLC_UNROLL
         for (int i = 0; i < 4; ++i) s = ELLC_ADD(s, fabsf(M[i * 4 + j]));
         l1 = fmaxf(l1, s);
     }
@@ -123,46 +174,52 @@ __host__ __device__ inline void se3_exp_pade_f(const float p[6], float T[16]) {
     int squarings = 0;
     if (l1 < 4.258730016922831e-001f) {
         m4_mul_f(M, M, A2);
-        m4_poly_f(1.f, A2, 0.f, nullptr, 0.f, nullptr, 60.f, tmp);
+        m4_poly_f<1>(1.f, A2, 0.f, A2, 0.f, A2, 60.f, tmp);
         m4_mul_f(M, tmp, U);
-        m4_poly_f(12.f, A2, 0.f, nullptr, 0.f, nullptr, 120.f, V);
+        m4_poly_f<1>(12.f, A2, 0.f, A2, 0.f, A2, 120.f, V);
     } else if (l1 < 1.880152677804762e+000f) {
         float A4[16];
         m4_mul_f(M, M, A2);
         m4_mul_f(A2, A2, A4);
-        m4_poly_f(1.f, A4, 420.f, A2, 0.f, nullptr, 15120.f, tmp);
+        m4_poly_f<2>(1.f, A4, 420.f, A2, 0.f, A2, 15120.f, tmp);
         m4_mul_f(M, tmp, U);
-        m4_poly_f(30.f, A4, 3360.f, A2, 0.f, nullptr, 30240.f, V);
+        m4_poly_f<2>(30.f, A4, 3360.f, A2, 0.f, A2, 30240.f, V);
     } else {
         float A[16], A4[16], A6[16];
         (void)frexpf(ELLC_DIV(l1, 3.925724783138660f), &squarings);
         if (squarings < 0) squarings = 0;
         const float sc = ldexpf(1.0f, squarings);
+        ELLC_UNROLL
         for (int i = 0; i < 16; ++i) A[i] = ELLC_DIV(M[i], sc);
         m4_mul_f(A, A, A2);
         m4_mul_f(A2, A2, A4);
         m4_mul_f(A4, A2, A6);
-        m4_poly_f(1.f, A6, 1512.f, A4, 277200.f, A2, 8648640.f, tmp);
+        m4_poly_f<3>(1.f, A6, 1512.f, A4, 277200.f, A2, 8648640.f, tmp);
         m4_mul_f(A, tmp, U);
-        m4_poly_f(56.f, A6, 25200.f, A4, 1995840.f, A2, 17297280.f, V);
+        m4_poly_f<3>(56.f, A6, 25200.f, A4, 1995840.f, A2, 17297280.f, V);
     }
     float num[16], den[16];
+    ELLC_UNROLL
     for (int i = 0; i < 16; ++i) { num[i] = ELLC_ADD(U[i], V[i]); den[i] = ELLC_ADD(-U[i], V[i]); }
     lu4_solve_f(den, num, T);
     for (int s = 0; s < squarings; ++s) {
         m4_mul_f(T, T, tmp);
+        ELLC_UNROLL
         for (int i = 0; i < 16; ++i) T[i] = tmp[i];
     }
 }
 
 // log of the rigid part of a 4x4 fp32 matrix -> fp32 6-vector (double evaluation, rounded once)
-__host__ __device__ inline void m4_log_f(const float T[16], float out[6]) {
+__host__ __device__ inline void m4_log_f(const float (&T)[16], float out[6]) {
     double R[9], t[3], o[6];
+    ELLC_UNROLL
     for (int i = 0; i < 3; ++i) {
+        ELLC_UNROLL
         for (int j = 0; j < 3; ++j) R[i * 3 + j] = (double)T[i * 4 + j];
         t[i] = (double)T[i * 4 + 3];
     }
     se3_log_d(R, t, o);
+    ELLC_UNROLL
     for (int i = 0; i < 6; ++i) out[i] = (float)o[i];
 }
 
@@ -180,6 +237,7 @@ __host__ __device__ inline void concat_origin_f(const float a[6], const float b[
     float Ta[16], Tb[16], Ti[16], T[16], I[16];
     se3_exp_pade_f(a, Ta);
     se3_exp_pade_f(b, Tb);
+    ELLC_UNROLL
     for (int i = 0; i < 16; ++i) I[i] = (i % 5 == 0) ? 1.f : 0.f;
     lu4_solve_f(Tb, I, Ti);
     m4_mul_f(Ta, Ti, T);
@@ -190,64 +248,91 @@ __host__ __device__ inline void concat_origin_f(const float a[6], const float b[
 __host__ __device__ inline void pose_to_rt_f(const float pose[6], float Rt[12]) {
     float T[16];
     se3_exp_pade_f(pose, T);
+    ELLC_UNROLL
     for (int i = 0; i < 12; ++i) Rt[i] = T[i];
 }
 
 // cv::Mat::inv() for a 6x6 CV_32F: partial-pivot LU on [A | I] in fp32 (each op individually rounded, as OpenCV's
 // scalar LUImpl<float>), pivot threshold FLT_EPSILON*10, back-substitution multiplying by the stored reciprocal.
 // Returns false and an all-zero inverse when singular (=> deltapose = 0, weightedPose = 0 < 1 => level ends).
-__host__ __device__ inline bool invert6_lu_f(const float Hin[36], float Hinv[36]) {
-    const int m = 6;
+__host__ __device__ inline bool invert6_lu_f(const float (&Hin)[36], float (&Hinv)[36]) {
+    constexpr int m = 6;
     float A[36], B[36];
+    ELLC_UNROLL
     for (int i = 0; i < 36; ++i) { A[i] = Hin[i]; B[i] = (i % 7 == 0) ? 1.f : 0.f; }
     const float eps = 1.1920929e-07f * 10;
+    bool ok = true;
+    ELLC_UNROLL
     for (int i = 0; i < m; ++i) {
         int k = i;
-        for (int j = i + 1; j < m; ++j)
-            if (fabsf(A[j * m + i]) > fabsf(A[k * m + i])) k = j;
-        if (fabsf(A[k * m + i]) < eps) {
-            for (int q = 0; q < 36; ++q) Hinv[q] = 0.f;
-            return false;
+        float best = fabsf(A[i * m + i]);
+        ELLC_UNROLL
+        for (int j = i + 1; j < m; ++j) {
+            const float v = fabsf(A[j * m + i]);
+            if (v > best) { best = v; k = j; }
         }
-        if (k != i) {
-            for (int j = i; j < m; ++j) { float tmp = A[i * m + j]; A[i * m + j] = A[k * m + j]; A[k * m + j] = tmp; }
-            for (int j = 0; j < m; ++j) { float tmp = B[i * m + j]; B[i * m + j] = B[k * m + j]; B[k * m + j] = tmp; }
+        if (best < eps) ok = false;                           // LUImpl returns 0 here; keep going branch-free, zero below
+        ELLC_UNROLL
+        for (int j = i + 1; j < m; ++j) {                     // swap rows i and k: columns i.. of A, all of B
+            const bool sw = (k == j);
+            ELLC_UNROLL
+            for (int c = i; c < m; ++c) {
+                const float a0 = A[i * m + c], a1 = A[j * m + c];
+                A[i * m + c] = sw ? a1 : a0; A[j * m + c] = sw ? a0 : a1;
+            }
+            ELLC_UNROLL
+            for (int c = 0; c < m; ++c) {
+                const float b0 = B[i * m + c], b1 = B[j * m + c];
+                B[i * m + c] = sw ? b1 : b0; B[j * m + c] = sw ? b0 : b1;
+            }
         }
         const float d = ELLC_DIV(-1.f, A[i * m + i]);
+        ELLC_UNROLL
         for (int j = i + 1; j < m; ++j) {
             const float alpha = ELLC_MUL(A[j * m + i], d);
+            ELLC_UNROLL
             for (int c = i + 1; c < m; ++c) A[j * m + c] = ELLC_ADD(A[j * m + c], ELLC_MUL(alpha, A[i * m + c]));
+            ELLC_UNROLL
             for (int c = 0; c < m; ++c) B[j * m + c] = ELLC_ADD(B[j * m + c], ELLC_MUL(alpha, B[i * m + c]));
         }
         A[i * m + i] = -d;
     }
-    for (int i = m - 1; i >= 0; --i)
+    ELLC_UNROLL
+    for (int i = m - 1; i >= 0; --i) {
+        ELLC_UNROLL
         for (int j = 0; j < m; ++j) {
             float s = B[i * m + j];
+            ELLC_UNROLL
             for (int c = i + 1; c < m; ++c) s = ELLC_SUB(s, ELLC_MUL(A[i * m + c], B[c * m + j]));
             B[i * m + j] = ELLC_MUL(s, A[i * m + i]);
         }
-    for (int q = 0; q < 36; ++q) Hinv[q] = B[q];
-    return true;
+    }
+    ELLC_UNROLL
+    for (int q = 0; q < 36; ++q) Hinv[q] = ok ? B[q] : 0.f;
+    return ok;
 }
 
 // hessianInv = hessian.inv(); updatePose()  -- src/PixelWisePyramid.cpp:451-491.
 // delta_i = -(sum_k Hinv[i][k] b[k]) with cv::gemm's double accumulator; weightedPose = sum |delta_i * weight_i|;
 // pose <- log(exp(delta) exp(pose)).  Returns false if the hessian was singular.
-__host__ __device__ inline bool solve_update_f(const float H[36], const float b[6], const float weight[6],
-                                               float pose[6], float delta[6], float* weighted_pose) {
+__host__ __device__ inline bool solve_update_f(const float (&H)[36], const float (&b)[6], const float (&weight)[6],
+                                               float (&pose)[6], float (&delta)[6], float* weighted_pose) {
     float Hinv[36];
     const bool ok = invert6_lu_f(H, Hinv);
+    ELLC_UNROLL
     for (int i = 0; i < 6; ++i) {
         double s = 0.0;
+        ELLC_UNROLL
         for (int k = 0; k < 6; ++k) s = ELLC_DADD(s, ELLC_DMUL((double)Hinv[i * 6 + k], (double)b[k]));
         delta[i] = -(float)s;
     }
     float wp = fabsf(ELLC_MUL(delta[0], weight[0]));
+    ELLC_UNROLL
     for (int i = 1; i < 6; ++i) wp = ELLC_ADD(wp, fabsf(ELLC_MUL(delta[i], weight[i])));
     *weighted_pose = wp;
     float np[6];
     concat_relative_f(delta, pose, np);
+    ELLC_UNROLL
     for (int i = 0; i < 6; ++i) pose[i] = np[i];
     return ok;
 }
