@@ -10,6 +10,7 @@
 //              count[4], rowcount / rowoff scratch
 // Uploads only mark slots dirty; the pyramid / texel / selection kernels run batched over all dirty slots right before
 // the next consumer (track, evaluate, read-back) -- a whole batch costs 4 (frames) + 6 (keyframes) launches.
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -38,7 +39,7 @@ struct ellc_handle {
     std::vector<int> fr_dirty, kf_dirty;
     // staging
     int* d_slots; int slots_cap;
-    ellc_pair* d_pairs; ellc_result* d_results; int pairs_cap;
+    ellc_pair* d_pairs; ellc_result* d_results; int* d_order; int pairs_cap;
     ellc_iter_trace* d_trace; int64_t trace_cap;
     float* d_small;                                    // 128 floats in/out for solve_update
     float* d_weight; int64_t weight_cap;
@@ -110,7 +111,7 @@ int ellc_destroy(ellc_handle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->fr_img); cudaFree(h->fr_tex); cudaFree(h->kf_img); cudaFree(h->kf_depth); cudaFree(h->kf_var);
     cudaFree(h->kf_mask); cudaFree(h->kf_geo); cudaFree(h->kf_pix); cudaFree(h->kf_count); cudaFree(h->kf_rowcount); cudaFree(h->kf_rowoff);
-    cudaFree(h->d_slots); cudaFree(h->d_pairs); cudaFree(h->d_results); cudaFree(h->d_trace); cudaFree(h->d_small);
+    cudaFree(h->d_slots); cudaFree(h->d_pairs); cudaFree(h->d_results); cudaFree(h->d_order); cudaFree(h->d_trace); cudaFree(h->d_small);
     cudaFree(h->d_weight);
     if (h->h_pin) cudaFreeHost(h->h_pin);
     if (h->ev_valid) { cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); }
@@ -211,11 +212,12 @@ static int stage_h2d(ellc_handle* h, void* dst, const void* src, size_t bytes) {
 
 static int ensure_pairs_cap(ellc_handle* h, int n, bool want_trace) {
     if (n > h->pairs_cap) {
-        cudaFree(h->d_pairs); cudaFree(h->d_results);
-        h->d_pairs = nullptr; h->d_results = nullptr; h->pairs_cap = 0;
+        cudaFree(h->d_pairs); cudaFree(h->d_results); cudaFree(h->d_order);
+        h->d_pairs = nullptr; h->d_results = nullptr; h->d_order = nullptr; h->pairs_cap = 0;
         int cap = n < 256 ? 256 : n;
         CU_TRY(h, cudaMalloc(&h->d_pairs, (size_t)cap * sizeof(ellc_pair)));
         CU_TRY(h, cudaMalloc(&h->d_results, (size_t)cap * sizeof(ellc_result)));
+        CU_TRY(h, cudaMalloc(&h->d_order, (size_t)cap * sizeof(int)));
         h->pairs_cap = cap;
     }
     if (want_trace) {
@@ -328,10 +330,23 @@ static int track_launch(ellc_handle* h, int n, const ellc_pair* pairs, bool want
     if (rc) return rc;
     rc = stage_h2d(h, h->d_pairs, pairs, (size_t)n * sizeof(ellc_pair));
     if (rc) return rc;
+    // Schedule: frame-major, keyframe-minor.  Pairs are independent, so the order is free; putting the K pairs of one
+    // frame on adjacent CTAs makes them share that frame's texel pyramid in L2 (and, with few keyframes, the keyframe
+    // selection lists stay L2-resident as well).  Results are still written at the caller's pair index.
+    {
+        std::vector<int> order(n);
+        for (int i = 0; i < n; ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+            if (pairs[a].frame_slot != pairs[b].frame_slot) return pairs[a].frame_slot < pairs[b].frame_slot;
+            return pairs[a].kf_slot < pairs[b].kf_slot;
+        });
+        rc = stage_h2d(h, h->d_order, order.data(), (size_t)n * sizeof(int));
+        if (rc) return rc;
+    }
     if (want_trace) CU_TRY(h, cudaMemsetAsync(h->d_trace, 0, (size_t)n * kLevels * ELLC_MAX_TRACE_ITERS * sizeof(ellc_iter_trace), h->stream));
     TrackParams p;
     fill_params(h, p);
-    p.pairs = h->d_pairs; p.results = h->d_results; p.trace = want_trace ? h->d_trace : nullptr; p.n_pairs = n;
+    p.pairs = h->d_pairs; p.order = h->d_order; p.results = h->d_results; p.trace = want_trace ? h->d_trace : nullptr; p.n_pairs = n;
     CU_TRY(h, cudaEventRecord(h->ev0, h->stream));
     const int l = launch_track(h->stream, p, pick_cluster(h, n), h->cfg.arithmetic == ELLC_ARITH_STRICT);
     if (l < 0) { h->err = std::string("track kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()); return ELLC_ERR_CUDA; }

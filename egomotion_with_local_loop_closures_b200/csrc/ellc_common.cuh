@@ -75,6 +75,7 @@ struct TrackParams {
     const int* count_pool;                                    // [kf_slot][kLevels]
     // work
     const ellc_pair* pairs;
+    const int* order;          // optional schedule: CTA cluster c tracks pairs[order[c]]
     ellc_result* results;
     ellc_iter_trace* trace;    // optional [pair][level][ELLC_MAX_TRACE_ITERS]
     int n_pairs;
@@ -83,6 +84,7 @@ struct TrackParams {
     int iter_limit;            // 0 = use max_iter
     int no_update;
     float* weight_out;         // optional display_weightimg of the evaluated level (cols x rows), evaluate-only mode
+    uint32_t zero_mask;        // always 0: an opaque zero the pixel loop uses to build ordering dependences
 };
 
 }  // namespace ellc
