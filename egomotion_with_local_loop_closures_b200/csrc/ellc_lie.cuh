@@ -337,4 +337,97 @@ __host__ __device__ inline bool solve_update_f(const float (&H)[36], const float
     return ok;
 }
 
+
+#ifdef __CUDACC__
+// ---- warp-cooperative K5 (device only) -------------------------------------------------------------------------------
+// The same LU as invert6_lu_f, with the six right-hand-side columns of [A | I] spread over lanes (lane % 6 owns one column
+// of the inverse) while every lane eliminates A redundantly: identical pivots, identical operations per entry, 1/4 of the
+// serial instruction count.  Returns column (lane % 6) of the inverse in col[0..5]; *ok as invert6_lu_f.
+__device__ inline void invert6_lu_warp(const float (&Hin)[36], int lane, float (&col)[6], bool* okp) {
+    constexpr int m = 6;
+    const int mycol = lane % 6;
+    float A[36], B[6];
+    ELLC_UNROLL
+    for (int i = 0; i < 36; ++i) A[i] = Hin[i];
+    ELLC_UNROLL
+    for (int i = 0; i < 6; ++i) B[i] = (i == mycol) ? 1.f : 0.f;
+    const float eps = 1.1920929e-07f * 10;
+    bool ok = true;
+    ELLC_UNROLL
+    for (int i = 0; i < m; ++i) {
+        int k = i;
+        float best = fabsf(A[i * m + i]);
+        ELLC_UNROLL
+        for (int j = i + 1; j < m; ++j) {
+            const float v = fabsf(A[j * m + i]);
+            if (v > best) { best = v; k = j; }
+        }
+        if (best < eps) ok = false;
+        ELLC_UNROLL
+        for (int j = i + 1; j < m; ++j) {
+            const bool sw = (k == j);
+            ELLC_UNROLL
+            for (int c = i; c < m; ++c) {
+                const float a0 = A[i * m + c], a1 = A[j * m + c];
+                A[i * m + c] = sw ? a1 : a0; A[j * m + c] = sw ? a0 : a1;
+            }
+            const float b0 = B[i], b1 = B[j];
+            B[i] = sw ? b1 : b0; B[j] = sw ? b0 : b1;
+        }
+        const float d = ELLC_DIV(-1.f, A[i * m + i]);
+        ELLC_UNROLL
+        for (int j = i + 1; j < m; ++j) {
+            const float alpha = ELLC_MUL(A[j * m + i], d);
+            ELLC_UNROLL
+            for (int c = i + 1; c < m; ++c) A[j * m + c] = ELLC_ADD(A[j * m + c], ELLC_MUL(alpha, A[i * m + c]));
+            B[j] = ELLC_ADD(B[j], ELLC_MUL(alpha, B[i]));
+        }
+        A[i * m + i] = -d;
+    }
+    ELLC_UNROLL
+    for (int i = m - 1; i >= 0; --i) {
+        float s = B[i];
+        ELLC_UNROLL
+        for (int c = i + 1; c < m; ++c) s = ELLC_SUB(s, ELLC_MUL(A[i * m + c], B[c]));
+        B[i] = ELLC_MUL(s, A[i * m + i]);
+    }
+    ELLC_UNROLL
+    for (int q = 0; q < 6; ++q) col[q] = ok ? B[q] : 0.f;
+    *okp = ok;
+}
+
+// solve_update_f executed by one full warp (all 32 lanes call it with the same arguments and get the same results).
+// Rt_pose is exp(hat(pose)) as computed for the current iteration (its 4th row is exactly [0 0 0 1]), so only exp(delta)
+// has to be evaluated for the composition.
+__device__ inline bool solve_update_warp(const float (&H)[36], const float (&b)[6], const float (&weight)[6],
+                                         const float (&Rt_pose)[12], float (&pose)[6], float (&delta)[6],
+                                         float* weighted_pose, int lane) {
+    float col[6];
+    bool ok;
+    invert6_lu_warp(H, lane, col, &ok);
+    // delta_i = -(sum_k Hinv[i][k] b[k]): lane k (< 6) holds Hinv[.][k]; products are exact in double, the sum runs k = 0..5
+    const double bk = (double)b[lane % 6];
+    ELLC_UNROLL
+    for (int i = 0; i < 6; ++i) {
+        const double term = __dmul_rn((double)col[i], bk);
+        double s = 0.0;
+        ELLC_UNROLL
+        for (int k = 0; k < 6; ++k) s = __dadd_rn(s, __shfl_sync(0xffffffffu, term, k));
+        delta[i] = -(float)s;
+    }
+    float wp = fabsf(ELLC_MUL(delta[0], weight[0]));
+    ELLC_UNROLL
+    for (int i = 1; i < 6; ++i) wp = ELLC_ADD(wp, fabsf(ELLC_MUL(delta[i], weight[i])));
+    *weighted_pose = wp;
+    float Ta[16], Tb[16], T[16];
+    se3_exp_pade_f(delta, Ta);
+    ELLC_UNROLL
+    for (int i = 0; i < 12; ++i) Tb[i] = Rt_pose[i];
+    Tb[12] = Tb[13] = Tb[14] = 0.f; Tb[15] = 1.f;
+    m4_mul_f(Ta, Tb, T);
+    m4_log_f(T, pose);
+    return ok;
+}
+#endif  // __CUDACC__
+
 }  // namespace ellc
