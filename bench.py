@@ -29,6 +29,16 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# Keep stdout for the ONE JSON line: libraries (NCCL's version banner, ...) write to fd 1 behind Python's back, so fd 1 is
+# pointed at stderr for the whole run and the result line goes to a private duplicate of the original stdout.
+_RESULT_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_RESULT_FD, (json.dumps(line) + "\n").encode())
+
+
 from egomotion_with_local_loop_closures_b200 import synth  # noqa: E402
 
 W, H = 640, 480
@@ -179,7 +189,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -212,7 +222,7 @@ def main():
     import torch
     import torch.distributed as dist
     from egomotion_with_local_loop_closures_b200 import capi
-    from egomotion_with_local_loop_closures_b200.sharding import gather_results, shard_pairs_by_keyframe
+    from egomotion_with_local_loop_closures_b200.sharding import gather_results, shard_pairs
 
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -225,13 +235,17 @@ def main():
     trk = capi.Tracker(cfg)
     stream = torch.cuda.ExternalStream(trk.stream(), device=torch.device("cuda", local_rank))
 
-    # global pair list = concatenation of all ranks' lists (keyframe ids offset per rank); sharding by keyframe affinity
-    # hands every rank exactly its own keyframes back -- the production path for a mixed list.
-    g_kf = np.concatenate([wl["kf_idx"] + r * args.keyframes for r in range(world)]) if world > 1 else wl["kf_idx"]
-    shards = shard_pairs_by_keyframe(g_kf, world)
-    my_idx = shards[rank]
+    # Global pair list = the sequence segments of all ranks (keyframe / frame ids offset per segment).  shard_pairs deals whole
+    # connected components (segments) to ranks, so every rank gets one segment back -- the production path for a mixed list.
     if world > 1:
-        assert len(my_idx) == n_pairs and np.all((g_kf[my_idx] // args.keyframes) == g_kf[my_idx][0] // args.keyframes)
+        g_kf = np.concatenate([wl["kf_idx"].astype(np.int64) + r * args.keyframes for r in range(world)])
+        g_fr = np.concatenate([wl["fr_idx"].astype(np.int64) + r * args.frames for r in range(world)])
+        shards = shard_pairs(g_kf, g_fr, world)
+        seg = [int(g_kf[s][0] // args.keyframes) for s in shards]
+        assert sorted(seg) == list(range(world)) and all(len(s) == n_pairs for s in shards)
+        my_idx = shards[seg.index(rank)]                       # this rank rendered segment `rank`
+    else:
+        my_idx = np.arange(n_pairs)
     n_total = n_pairs * world
 
     # pinned host copies (e2e uploads) -----------------------------------------------------------------------------
@@ -367,11 +381,11 @@ def main():
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": "pair_sweep_640x480", "width": W, "height": H, "keyframes_per_gpu": args.keyframes,
                            "frames_per_gpu": args.frames, "pairs_per_gpu_per_step": n_pairs, "pairs_per_frame": args.pairs_per_frame,
-                           "arithmetic": args.arith, "parallelism": f"pairs sharded by keyframe affinity x{world}, result all-gather",
+                           "arithmetic": args.arith, "parallelism": f"pair list sharded by connected components (sequence segments) x{world}, NCCL all-gather of 256 B result records",
                            "l2": "inputs (%.0f MB per step per GPU) exceed the 126 MB L2; no flush" % (h2d_bytes / 1e6),
                            "setup_bytes_per_step": setup_bytes(args.frames, args.keyframes) * world, "setup_seconds": setup_s},
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
-        print(json.dumps(line), flush=True)
+        emit(line)
     trk.close()
     if world > 1:
         dist.barrier()

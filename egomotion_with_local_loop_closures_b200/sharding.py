@@ -26,6 +26,52 @@ def shard_pairs_by_keyframe(kf_ids, world_size):
     return [np.nonzero(ranks == r)[0] for r in range(world_size)]
 
 
+def shard_pairs(kf_ids, frame_ids, world_size):
+    """Shard a pair list so that ranks share as little as possible.
+
+    Pairs form a bipartite graph keyframes <-> frames.  Its connected components (a stretch of the sequence: frames and
+    the keyframes they are matched against) are independent in DATA as well as in compute, so whole components are dealt
+    to the least-loaded rank, largest first; a component bigger than 1.5x the fair share is split by keyframe affinity
+    (its frames are then prepared on more than one rank).  Deterministic; returns one index array per rank, each in the
+    original pair order."""
+    kf_ids = np.asarray(kf_ids, np.int64)
+    frame_ids = np.asarray(frame_ids, np.int64)
+    n = len(kf_ids)
+    if n == 0:
+        return [np.zeros(0, np.int64) for _ in range(world_size)]
+    ku, kinv = np.unique(kf_ids, return_inverse=True)
+    fu, finv = np.unique(frame_ids, return_inverse=True)
+    parent = np.arange(len(ku) + len(fu))
+
+    def find(x):
+        while parent[x] != x:
+            parent[x] = parent[parent[x]]
+            x = parent[x]
+        return x
+
+    for a, b in zip(kinv, finv + len(ku)):
+        ra, rb = find(a), find(b)
+        if ra != rb:
+            parent[max(ra, rb)] = min(ra, rb)
+    comp = np.array([find(a) for a in kinv])
+    cu, cinv, ccount = np.unique(comp, return_inverse=True, return_counts=True)
+    fair = -(-n // world_size)
+    load = np.zeros(world_size, np.int64)
+    rank_of = np.full(n, -1, np.int64)
+    for c in np.lexsort((cu, -ccount)):
+        idx = np.nonzero(cinv == c)[0]
+        if len(idx) > 1.5 * fair and world_size > 1:
+            for r, sub in enumerate(shard_pairs_by_keyframe(kf_ids[idx], world_size)):
+                tgt = int(np.lexsort((np.arange(world_size), load))[0]) if len(sub) else 0
+                rank_of[idx[sub]] = tgt
+                load[tgt] += len(sub)
+        else:
+            tgt = int(np.lexsort((np.arange(world_size), load))[0])
+            rank_of[idx] = tgt
+            load[tgt] += len(idx)
+    return [np.nonzero(rank_of == r)[0] for r in range(world_size)]
+
+
 def gather_results(local_records, local_indices, n_total, group=None, device=None):
     """All-gather variable-length shards of fixed-size records and restore the global pair order.
 

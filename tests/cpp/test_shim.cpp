@@ -1,0 +1,70 @@
+// Drives the C++ host shim exactly the way the reference's main loop drives its tracker (src/main.cpp:199-384):
+// one keyframe, consecutive frames, GetImagePoseEstimate initialised from the previous frame's world pose.
+// Input blob (written by tests/test_host_shim.py): int32 w, h, n_frames; f32 fx fy cx cy; u8 kf image; 4 depth levels;
+// 4 variance levels; n_frames u8 images.  Prints one line per result; the pytest side compares with the CPU oracle.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "DepthPropagation.h"
+#include "ExternVariable.h"
+#include "Frame.h"
+#include "ImageFunc.h"
+#include "PixelWisePyramid.h"
+
+static void rd(FILE* f, void* p, size_t n) { if (fread(p, 1, n, f) != n) { fprintf(stderr, "short read\n"); exit(2); } }
+
+int main(int argc, char** argv) {
+    if (argc < 2) { fprintf(stderr, "usage: test_shim blob [--link-only]\n"); return 2; }
+    if (argc > 2) { printf("link ok\n"); return 0; }
+    FILE* f = fopen(argv[1], "rb");
+    if (!f) return 2;
+    int w, h, n; float k[4];
+    rd(f, &w, 4); rd(f, &h, 4); rd(f, &n, 4); rd(f, k, 16);
+    util::configure(w, h, k[0], k[1], k[2], k[3]);
+    std::vector<unsigned char> img((size_t)w * h);
+    rd(f, img.data(), img.size());
+    try {
+        frame kf(img.data(), w, h);
+        depthMap dm;
+        dm.keyFrame = &kf;
+        for (int l = 0; l < 4; ++l) rd(f, kf.depth_pyramid[l].ptr<float>(0), (size_t)(w >> l) * (h >> l) * 4);
+        for (int l = 0; l < 4; ++l) rd(f, dm.depthvararrptr[l], (size_t)(w >> l) * (h >> l) * 4);
+        dm.markDepthUpdated();
+        printf("pyr %d %d %d %d\n", kf.image_pyramid[1].cols, kf.image_pyramid[1].rows, kf.image_pyramid[3].cols, kf.image_pyramid[3].rows);
+        frame* prev = &kf;
+        std::vector<frame*> frames;
+        for (int i = 0; i < n; ++i) {
+            rd(f, img.data(), img.size());
+            frame* cur = new frame(img.data(), w, h);
+            frames.push_back(cur);
+            float init[6] = {0, 0, 0, 0, 0, 0};
+            std::vector<float> p = GetImagePoseEstimate(&kf, cur, i + 2, &dm, prev, init);
+            printf("pose %d %.9g %.9g %.9g %.9g %.9g %.9g\n", i, p[0], p[1], p[2], p[3], p[4], p[5]);
+            printf("world %d %.9g %.9g %.9g %.9g %.9g %.9g\n", i, cur->poseWrtWorld[0], cur->poseWrtWorld[1], cur->poseWrtWorld[2],
+                   cur->poseWrtWorld[3], cur->poseWrtWorld[4], cur->poseWrtWorld[5]);
+            printf("post %d %d %d %d %d %d\n", i, kf.pyrLevel, cur->pyrLevel, kf.no_nonZeroDepthPts, cur->gradientx.cols, kf.mask.rows);
+            prev = cur;
+        }
+        // caller-driven iterations through the PixelWisePyramid surface (src/ImageFunc.cpp:163-253) at level 2
+        kf.updationOnPyrChange(2);
+        frames[0]->updationOnPyrChange(2, false);
+        float pose[6] = {0, 0, 0, 0, 0, 0};
+        PixelWisePyramid pw(&kf, frames[0], pose, &dm);
+        pw.pose = pose;
+        for (int it = 0; it < 3; ++it) {
+            pw.calculatePixelWiseParallel();
+            printf("iter %d %.9g %.9g %.9g %.9g %.9g %.9g wp %.9g res %.9g H00 %.9g\n", it, pose[0], pose[1], pose[2], pose[3], pose[4], pose[5],
+                   pw.weightedPose, pw.residualSum, pw.hessian.ptr<float>(0)[0]);
+        }
+        printf("count2 %d\n", kf.no_nonZeroDepthPts);
+        for (frame* c : frames) delete c;
+    } catch (const std::exception& e) {
+        fprintf(stderr, "shim error: %s\n", e.what());
+        ellc_host::shutdown();
+        return 3;
+    }
+    ellc_host::shutdown();
+    fclose(f);
+    return 0;
+}

@@ -1,0 +1,85 @@
+"""The C++ host shim (reference class surface on top of the C-ABI): builds on CPU, runs and matches the oracle on GPU."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "egomotion_with_local_loop_closures_b200")
+EXE = os.path.join(ROOT, "tests", "cpp", "test_shim")
+
+
+def build_shim():
+    import __graft_entry__ as g
+    g.build()
+    src = [os.path.join(ROOT, "tests", "cpp", "test_shim.cpp"), os.path.join(PKG, "host", "HostShim.cpp")]
+    deps = src + [os.path.join(PKG, "libellc_gn.so")]
+    if not os.path.exists(EXE) or any(os.path.getmtime(s) > os.path.getmtime(EXE) for s in deps):
+        subprocess.check_call(["g++", "-std=c++11", "-O2", "-pthread", "-I", os.path.join(PKG, "host"), "-o", EXE] + src +
+                              ["-L", PKG, "-lellc_gn", "-Wl,-rpath," + PKG])
+    return EXE
+
+
+def test_shim_builds_and_links():
+    exe = build_shim()
+    out = subprocess.check_output([exe, "none", "--link-only"], text=True)
+    assert "link ok" in out
+
+
+@pytest.mark.gpu
+def test_shim_tracks_like_the_reference_driver(tmp_path, oracle_mod):
+    from egomotion_with_local_loop_closures_b200 import synth
+    from tests.helpers import oracle_config
+    exe = build_shim()
+    w, h, n = 320, 240, 3
+    scene = synth.SynthScene(w, h)
+    kf = scene.keyframe(noise_seed=5)
+    T = synth.smooth_trajectory(n + 1, seed_pose=3)
+    frames = [scene.render(T[i + 1], noise_seed=50 + i) for i in range(n)]
+    k = synth.intrinsics(w, h)
+    blob = tmp_path / "case.bin"
+    with open(blob, "wb") as f:
+        f.write(struct.pack("<iii4f", w, h, n, float(k["fx"]), float(k["fy"]), float(k["cx"]), float(k["cy"])))
+        f.write(kf["image"].tobytes())
+        for l in range(4):
+            f.write(np.ascontiguousarray(kf["depth"][l], np.float32).tobytes())
+        for l in range(4):
+            f.write(np.ascontiguousarray(kf["var"][l], np.float32).tobytes())
+        for im in frames:
+            f.write(im.tobytes())
+    out = subprocess.check_output([exe, str(blob)], text=True)
+    lines = [l.split() for l in out.strip().splitlines()]
+    got_pose = {int(l[1]): np.array(l[2:8], np.float64) for l in lines if l[0] == "pose"}
+    got_world = {int(l[1]): np.array(l[2:8], np.float64) for l in lines if l[0] == "world"}
+    post = [l for l in lines if l[0] == "post"]
+    assert [l for l in lines if l[0] == "pyr"][0][1:] == [str(w // 2), str(h // 2), str(w // 8), str(h // 8)]
+
+    case = dict(width=w, height=h)
+    ocfg = oracle_config(oracle_mod, case)
+    kf_world = np.zeros(6, np.float32)
+    prev_world = kf_world.copy()
+    for i in range(n):
+        init = oracle_mod.concat_origin(prev_world, kf_world)                 # src/ImageFunc.cpp:106
+        opose, otr = oracle_mod.track(ocfg, kf["image"], frames[i], kf["depth"], kf["var"], init)
+        world = oracle_mod.concat_relative(opose, kf_world)                   # src/ImageFunc.cpp:306
+        assert np.abs(got_pose[i] - opose).max() < 1e-4 and np.abs(got_pose[i] - opose).max() < 2e-6
+        assert np.abs(got_world[i] - world).max() < 2e-6
+        gt = synth.relative_pose(T[i + 1], np.eye(4))
+        assert np.abs(got_pose[i] - gt).max() < 3e-3
+        assert post[i][2:] == ["0", "0", str(otr["n_selected"][0]), str(w), str(h)]          # level-0 post-conditions
+        prev_world = world
+    # caller-driven iterations through PixelWisePyramid at level 2
+    kpyr = oracle_mod.image_pyramid(kf["image"]); cpyr = oracle_mod.image_pyramid(frames[0])
+    pose = np.zeros(6, np.float32)
+    iters = [l for l in lines if l[0] == "iter"]
+    for it in range(3):
+        o = oracle_mod.gn_evaluate(ocfg, 2, kpyr[2], cpyr[2], kf["depth"][2], kf["var"][2], pose)
+        Hinv, _ = oracle_mod.invert6(o["H"])
+        pose, delta, wp = oracle_mod.update_pose(ocfg, Hinv, o["b"], pose)
+        g = iters[it]
+        assert np.abs(np.array(g[2:8], np.float64) - pose).max() < 2e-6
+        assert abs(float(g[11]) - o["res_sum_f64"]) <= 1e-5 * o["res_sum_f64"]
+        assert abs(float(g[13]) - o["H_f64"][0, 0]) <= 1e-5 * o["H_f64"][0, 0]
+    assert [l for l in lines if l[0] == "count2"][0][1] == str(int((kf["depth"][2] > 0).sum()))

@@ -7,7 +7,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from egomotion_with_local_loop_closures_b200 import capi
-from egomotion_with_local_loop_closures_b200.sharding import gather_results, shard_pairs_by_keyframe
+from egomotion_with_local_loop_closures_b200.sharding import gather_results, shard_pairs, shard_pairs_by_keyframe
 
 
 def test_shard_by_keyframe_properties():
@@ -25,6 +25,29 @@ def test_shard_by_keyframe_properties():
         sizes = np.array([len(s) for s in shards])
         assert sizes.max() - sizes.min() <= np.bincount(kf).max()            # balanced up to one keyframe
     assert [len(s) for s in shard_pairs_by_keyframe([], 2)] == [0, 0]
+
+
+def test_shard_pairs_keeps_sequence_segments_together():
+    # 4 independent segments (keyframes 8g..8g+7, frames 100g..100g+63, every frame vs 3 keyframes of its segment)
+    rng = np.random.default_rng(1)
+    kf, fr = [], []
+    for g in range(4):
+        for f in range(64):
+            for k in rng.choice(8, 3, replace=False):
+                kf.append(8 * g + k); fr.append(100 * g + f)
+    perm = rng.permutation(len(kf))
+    kf, fr = np.array(kf)[perm], np.array(fr)[perm]
+    for world in (1, 2, 4):
+        shards = shard_pairs(kf, fr, world)
+        assert sorted(np.concatenate(shards).tolist()) == list(range(len(kf)))
+        assert [len(s) for s in shards] == [len(kf) // world] * world
+        for s in shards:
+            assert np.all(np.diff(s) > 0)
+            segs = set((kf[s] // 8).tolist())
+            assert segs == set((fr[s] // 100).tolist()) and len(segs) == 4 // world      # whole segments, no frame shared
+    # one giant component falls back to keyframe affinity
+    shards = shard_pairs(np.arange(40) % 5, np.zeros(40, int), 2)
+    assert sorted(np.concatenate(shards).tolist()) == list(range(40)) and min(len(s) for s in shards) >= 16
 
 
 def _worker(rank, world, port, n_total, ret):
