@@ -166,7 +166,8 @@ int ellc_create(const ellc_config* cfg, ellc_handle** out) {
     const int64_t img = h->geo.img_off[kLevels], win = h->geo.win_off[kLevels];
     const int64_t nf = cfg->max_frames, nk = cfg->max_keyframes;
     CR_TRY(cudaMalloc(&h->fr_img, nf * img));
-    CR_TRY(cudaMalloc(&h->fr_tex, nf * win * sizeof(uint32_t)));
+    CR_TRY(cudaMalloc(&h->fr_tex, nf * (win + kTexPad) * sizeof(uint32_t)));
+    CR_TRY(cudaMemsetAsync(h->fr_tex, 0, nf * (win + kTexPad) * sizeof(uint32_t), h->stream));   // zero texel of every slot
     CR_TRY(cudaMalloc(&h->kf_img, nk * img));
     CR_TRY(cudaMalloc(&h->kf_depth, nk * win * sizeof(float)));
     CR_TRY(cudaMalloc(&h->kf_var, nk * win * sizeof(float)));
@@ -236,7 +237,7 @@ static int prepare_frames_impl(ellc_handle* h, int n, const int* slots) {
     int rc = stage_h2d(h, h->d_slots, slots, (size_t)n * sizeof(int));
     if (rc) return rc;
     h->launches += launch_pyramid(h->stream, h->fr_img, h->geo.img_off[kLevels], h->d_slots, n, h->geo);
-    h->launches += launch_pack_tex(h->stream, h->fr_img, h->geo.img_off[kLevels], h->fr_tex, h->geo.win_off[kLevels],
+    h->launches += launch_pack_tex(h->stream, h->fr_img, h->geo.img_off[kLevels], h->fr_tex, h->geo.win_off[kLevels] + kTexPad,
                                    h->d_slots, n, h->geo);
     CU_TRY(h, cudaGetLastError());
     for (int i = 0; i < n; ++i) h->fr_state[slots[i]] = 2;
@@ -286,7 +287,7 @@ static void fill_params(const ellc_handle* h, TrackParams& p) {
     for (int i = 0; i < 6; ++i) p.weight[i] = h->cfg.weight[i];
     p.stop_threshold = h->cfg.stop_threshold;
     p.jacobian_at_warped = h->cfg.jacobian_at_warped;
-    p.tex_pool = h->fr_tex; p.tex_slot_stride = h->geo.win_off[kLevels];
+    p.tex_pool = h->fr_tex; p.tex_slot_stride = h->geo.win_off[kLevels] + kTexPad;
     p.geo_pool = h->kf_geo; p.pix_pool = h->kf_pix; p.rec_slot_stride = h->geo.win_off[kLevels];
     p.count_pool = h->kf_count;
     p.level_hi = kLevels - 1; p.level_lo = 0;
@@ -533,7 +534,7 @@ int ellc_read_frame_level(ellc_handle* h, int32_t slot, int32_t level, uint8_t* 
     const size_t npx = (size_t)g.cols[level] * g.rows[level];
     if (gradx || grady) {
         tex.resize(npx);
-        CU_TRY(h, cudaMemcpyAsync(tex.data(), h->fr_tex + (int64_t)slot * g.win_off[kLevels] + g.win_off[level], npx * 4,
+        CU_TRY(h, cudaMemcpyAsync(tex.data(), h->fr_tex + (int64_t)slot * (g.win_off[kLevels] + kTexPad) + kTexPad + g.win_off[level], npx * 4,
                                   cudaMemcpyDeviceToHost, h->stream));
     }
     CU_TRY(h, cudaStreamSynchronize(h->stream));

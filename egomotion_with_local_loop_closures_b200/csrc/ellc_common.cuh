@@ -38,6 +38,7 @@ __host__ __device__ inline int selpix_i(SelPix p) { return (int)(p >> 22); }
 __host__ __device__ inline uint32_t tex_pack(int I, int gx2, int gy2) {
     return (uint32_t)I | (((uint32_t)gx2 & 0xfffu) << 8) | (((uint32_t)gy2 & 0xfffu) << 20);
 }
+constexpr int kTexPad = 4;      // words reserved at the start of every frame slot of the texel pool; word 0 stays zero
 __host__ __device__ inline int tex_I(uint32_t w) { return (int)(w & 0xffu); }
 __host__ __device__ inline int tex_gx2(uint32_t w) { return ((int)(w << 12)) >> 20; }
 __host__ __device__ inline int tex_gy2(uint32_t w) { return ((int)w) >> 20; }

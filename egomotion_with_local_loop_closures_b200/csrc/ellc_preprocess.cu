@@ -83,7 +83,7 @@ pack_tex_kernel(const uint8_t* __restrict__ img_pool, int64_t img_slot_stride, u
     if (y == 0) gy2 = 2 * ((int)r[stride + x] - c);
     else if (y == rows - 1) gy2 = 2 * (c - (int)r[x - stride]);
     else gy2 = (int)r[stride + x] - (int)r[x - stride];
-    tex_pool[(int64_t)slot * tex_slot_stride + gid] = tex_pack(c, gx2, gy2);
+    tex_pool[(int64_t)slot * tex_slot_stride + kTexPad + gid] = tex_pack(c, gx2, gy2);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
