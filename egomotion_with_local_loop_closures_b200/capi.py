@@ -12,7 +12,7 @@ import numpy as np
 LEVELS = 4
 MAX_TRACE_ITERS = 16
 ARITH_FAST, ARITH_STRICT = 0, 1
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libellc_gn.so")
+_LIB_PATH = os.environ.get("ELLC_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libellc_gn.so")
 
 
 class EllcError(RuntimeError):
