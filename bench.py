@@ -229,7 +229,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     k = synth.intrinsics(W, H)
     cfg = capi.default_config(W, H, fx=float(k["fx"]), fy=float(k["fy"]), cx=float(k["cx"]), cy=float(k["cy"]),
-                              max_keyframes=args.keyframes, max_frames=args.frames, device=local_rank,
+                              max_keyframes=2 * args.keyframes, max_frames=2 * args.frames, device=local_rank,
                               arithmetic=capi.ARITH_STRICT if args.arith == "strict" else capi.ARITH_FAST,
                               ctas_per_pair=args.cluster)
     trk = capi.Tracker(cfg)
@@ -267,13 +267,15 @@ def main():
         sum(a.nbytes for d in h_kf_var for a in d) + n_pairs * capi.PAIR_DTYPE.itemsize
     d2h_bytes = n_pairs * capi.RESULT_DTYPE.itemsize
 
-    def upload_all():
+    def upload_all(half=0):
+        ko, fo = half * args.keyframes, half * args.frames
         for i in range(args.keyframes):
-            trk.upload_keyframe(i, h_kf_img[i], h_kf_depth[i], h_kf_var[i])
+            trk.upload_keyframe(ko + i, h_kf_img[i], h_kf_depth[i], h_kf_var[i])
         for i in range(args.frames):
-            trk.upload_frame(i, h_frames[i])
+            trk.upload_frame(fo + i, h_frames[i])
 
     pairs = trk.make_pairs(wl["kf_idx"], wl["fr_idx"], wl["init"])
+    pairs_half = [pairs, trk.make_pairs(wl["kf_idx"] + args.keyframes, wl["fr_idx"] + args.frames, wl["init"])]
     fr_slots = np.arange(args.frames, dtype=np.int32)
     kf_slots = np.arange(args.keyframes, dtype=np.int32)
 
@@ -303,29 +305,54 @@ def main():
         err, = cudart.cudaMemcpy(dst_tensor.data_ptr(), src_ptr, nbytes, cudart.cudaMemcpyKind.cudaMemcpyDeviceToDevice)
         assert int(err) == 0
 
+    # e2e: every step uploads its inputs from pinned host memory and downloads its result records.  Steps alternate
+    # between two halves of the slot pools, so the uploads of step k+1 (copy stream) overlap the kernels of step k;
+    # the results of step k are fetched while step k+1 runs.
+    e2e_state = {"k": 0, "pending": None, "last": None}
+
     def step_e2e():
-        upload_all()
-        return trk.track_batch(pairs)
+        half = e2e_state["k"] & 1
+        t0 = time.perf_counter()
+        upload_all(half)
+        t1 = time.perf_counter()
+        dptr = trk.track_batch_async(pairs_half[half])
+        e2e_state["host_upload_ms"] = e2e_state.get("host_upload_ms", 0.0) + 1e3 * (t1 - t0)
+        e2e_state["host_launch_ms"] = e2e_state.get("host_launch_ms", 0.0) + 1e3 * (time.perf_counter() - t1)
+        if e2e_state["pending"] is not None:
+            e2e_state["last"] = trk.results_download(e2e_state["pending"], n_pairs)
+        e2e_state["pending"] = dptr
+        e2e_state["k"] += 1
+        return e2e_state["last"]
+
+    def drain_e2e():
+        if e2e_state["pending"] is not None:
+            e2e_state["last"] = trk.results_download(e2e_state["pending"], n_pairs)
+            e2e_state["pending"] = None
+        return e2e_state["last"]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup, sample_clocks=False):
+    def timed(fn, steps, warmup, sample_clocks=False, drain=None):
         res = None
-        for _ in range(warmup):
-            res = fn()
-        barrier()
         clk = ClockSampler(local_rank) if sample_clocks else None
         if clk:
-            clk.start()
+            clk.start()                                   # sampled over warm-up + timed steps (the same load)
+        for _ in range(warmup):
+            res = fn()
+        if drain:
+            res = drain()
+        barrier()
         kernel_ms.clear()
         trk.reset_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(steps):
             res = fn()
+        if drain:
+            res = drain()
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
@@ -357,9 +384,12 @@ def main():
 
     e2e = None
     if not args.no_e2e:
-        ems, eres, _, _ = timed(step_e2e, args.steps, max(1, args.warmup))
+        ems, eres, _, _ = timed(step_e2e, args.steps, max(1, args.warmup), drain=drain_e2e)
         e2e = {"value": n_total * args.steps / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes) * world,
-               "d2h_bytes_per_step": int(d2h_bytes) * world, "ms_per_step": ems / args.steps}
+               "d2h_bytes_per_step": int(d2h_bytes) * world, "ms_per_step": ems / args.steps,
+               "host_enqueue_ms_per_step": {"uploads": e2e_state.get("host_upload_ms", 0.0) / max(1, e2e_state["k"]),
+                                            "track_launch": e2e_state.get("host_launch_ms", 0.0) / max(1, e2e_state["k"])},
+               "pipelining": "2 slot halves alternate; uploads of step k+1 on the copy stream overlap the kernels of step k"}
         assert np.array_equal(eres["pose"], res["pose"]), "e2e and resident paths disagree"
 
     cpu_baseline = None

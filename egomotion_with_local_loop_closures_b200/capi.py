@@ -61,9 +61,10 @@ assert PAIR_DTYPE.itemsize == 36 and RESULT_DTYPE.itemsize == 256 and TRACE_DTYP
 SYMBOLS = ["ellc_default_config", "ellc_create", "ellc_destroy", "ellc_last_error_string", "ellc_version",
            "ellc_upload_frame", "ellc_upload_keyframe", "ellc_frame_image_devptr", "ellc_keyframe_devptrs",
            "ellc_prepare_frames", "ellc_prepare_keyframes", "ellc_track_batch", "ellc_track_batch_async",
+           "ellc_results_download",
            "ellc_synchronize", "ellc_gn_evaluate", "ellc_solve_update", "ellc_read_frame_level",
            "ellc_read_keyframe_level", "ellc_level_dims", "ellc_concat_relative", "ellc_concat_origin",
-           "ellc_se3_exp", "ellc_launch_count", "ellc_reset_launch_count", "ellc_stream", "ellc_last_track_kernel_ms"]
+           "ellc_se3_exp", "ellc_launch_count", "ellc_reset_launch_count", "ellc_stream", "ellc_stream_of", "ellc_last_track_kernel_ms"]
 
 _lib = None
 
@@ -91,6 +92,7 @@ def lib():
         L.ellc_track_batch.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ellc_track_batch_async.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]
         L.ellc_synchronize.argtypes = [C.c_void_p]
+        L.ellc_results_download.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         L.ellc_gn_evaluate.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ellc_solve_update.argtypes = [C.c_void_p] + [C.c_void_p] * 5 + [C.POINTER(C.c_float)]
         L.ellc_read_frame_level.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -104,6 +106,8 @@ def lib():
         L.ellc_reset_launch_count.argtypes = [C.c_void_p]
         L.ellc_stream.restype = C.c_void_p
         L.ellc_stream.argtypes = [C.c_void_p]
+        L.ellc_stream_of.restype = C.c_void_p
+        L.ellc_stream_of.argtypes = [C.c_void_p, C.c_int32]
         L.ellc_last_track_kernel_ms.restype = C.c_float
         L.ellc_last_track_kernel_ms.argtypes = [C.c_void_p]
         _lib = L
@@ -242,6 +246,11 @@ class Tracker:
         self._chk(lib().ellc_track_batch_async(self._h, len(pairs), _p(pairs), C.byref(dres)))
         return dres.value
 
+    def results_download(self, device_ptr, n):
+        res = np.zeros(n, RESULT_DTYPE)
+        self._chk(lib().ellc_results_download(self._h, device_ptr, n, _p(res)))
+        return res
+
     def gn_evaluate(self, kf_slot, frame_slot, level, pose, want_weights=False):
         pose = np.ascontiguousarray(pose, np.float32)
         out = np.zeros(1, TRACE_DTYPE)
@@ -286,6 +295,9 @@ class Tracker:
 
     def stream(self):
         return lib().ellc_stream(self._h)
+
+    def stream_of(self, which):
+        return lib().ellc_stream_of(self._h, which)
 
     def last_track_kernel_ms(self):
         return lib().ellc_last_track_kernel_ms(self._h)

@@ -28,8 +28,15 @@ struct ellc_handle {
     Geometry geo;
     LevelK K[kLevels];
     int rows_total;
-    cudaStream_t stream;
+    cudaStream_t stream;                               // compute: prepare kernels, track kernel, small staging copies
+    cudaStream_t copy_stream;                          // H2D uploads of images / depth / variance (overlap with compute)
+    cudaStream_t d2h_stream;                           // result downloads of finished batches
     cudaEvent_t ev0, ev1;
+    cudaEvent_t up_ev;                                 // re-recorded after every upload on copy_stream
+    bool uploads_pending;
+    cudaEvent_t batch_ev[4];                           // completion of the last 4 track batches (ring by sequence number)
+    long long batch_seq, batch_done_seq;               // last enqueued / last known-complete batch
+    std::vector<long long> fr_reader, kf_reader;       // sequence number of the last batch that reads each slot
     bool ev_valid;
     // pools
     uint8_t* fr_img; uint32_t* fr_tex;
@@ -39,11 +46,11 @@ struct ellc_handle {
     std::vector<int> fr_dirty, kf_dirty;
     // staging
     int* d_slots; int slots_cap;
-    ellc_pair* d_pairs; ellc_result* d_results; int* d_order; int pairs_cap;
+    ellc_pair* d_pairs; ellc_result* d_results; ellc_result* d_results2[2]; int* d_order; int pairs_cap;
     ellc_iter_trace* d_trace; int64_t trace_cap;
     float* d_small;                                    // 128 floats in/out for solve_update
     float* d_weight; int64_t weight_cap;
-    void* h_pin; size_t pin_cap, pin_used;             // pinned bump arena for small H2D payloads
+    void* h_pin; void* d_pin; size_t pin_cap, pin_used;             // pinned bump arena for small H2D payloads
     std::string err;
     int64_t launches;
 };
@@ -109,13 +116,20 @@ int ellc_destroy(ellc_handle* h) {
     if (!h) return ELLC_OK;
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+    if (h->d2h_stream) cudaStreamSynchronize(h->d2h_stream);
     cudaFree(h->fr_img); cudaFree(h->fr_tex); cudaFree(h->kf_img); cudaFree(h->kf_depth); cudaFree(h->kf_var);
     cudaFree(h->kf_mask); cudaFree(h->kf_geo); cudaFree(h->kf_pix); cudaFree(h->kf_count); cudaFree(h->kf_rowcount); cudaFree(h->kf_rowoff);
-    cudaFree(h->d_slots); cudaFree(h->d_pairs); cudaFree(h->d_results); cudaFree(h->d_order); cudaFree(h->d_trace); cudaFree(h->d_small);
+    cudaFree(h->d_slots); cudaFree(h->d_pairs); cudaFree(h->d_results2[0]); cudaFree(h->d_results2[1]); cudaFree(h->d_order); cudaFree(h->d_trace); cudaFree(h->d_small);
     cudaFree(h->d_weight);
     if (h->h_pin) cudaFreeHost(h->h_pin);
-    if (h->ev_valid) { cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); }
+    if (h->ev_valid) {
+        cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->up_ev);
+        for (int i = 0; i < 4; ++i) cudaEventDestroy(h->batch_ev[i]);
+    }
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
     delete h;
     return ELLC_OK;
 }
@@ -160,9 +174,15 @@ int ellc_create(const ellc_config* cfg, ellc_handle** out) {
     } while (0)
     CR_TRY(cudaSetDevice(cfg->device));
     CR_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CR_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    CR_TRY(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
     CR_TRY(cudaEventCreate(&h->ev0));
     CR_TRY(cudaEventCreate(&h->ev1));
+    CR_TRY(cudaEventCreateWithFlags(&h->up_ev, cudaEventDisableTiming));
+    for (int i = 0; i < 4; ++i) CR_TRY(cudaEventCreateWithFlags(&h->batch_ev[i], cudaEventDisableTiming));
     h->ev_valid = true;
+    h->fr_reader.assign(cfg->max_frames, 0);
+    h->kf_reader.assign(cfg->max_keyframes, 0);
     const int64_t img = h->geo.img_off[kLevels], win = h->geo.win_off[kLevels];
     const int64_t nf = cfg->max_frames, nk = cfg->max_keyframes;
     CR_TRY(cudaMalloc(&h->fr_img, nf * img));
@@ -180,8 +200,9 @@ int ellc_create(const ellc_config* cfg, ellc_handle** out) {
     h->slots_cap = (int)(nf > nk ? nf : nk);
     CR_TRY(cudaMalloc(&h->d_slots, 2 * h->slots_cap * sizeof(int)));
     CR_TRY(cudaMalloc(&h->d_small, 128 * sizeof(float)));
-    h->pin_cap = 1 << 20;
-    CR_TRY(cudaMallocHost(&h->h_pin, h->pin_cap));
+    h->pin_cap = 8 << 20;
+    CR_TRY(cudaHostAlloc(&h->h_pin, h->pin_cap, cudaHostAllocMapped));
+    CR_TRY(cudaHostGetDevicePointer(&h->d_pin, h->h_pin, 0));
     h->pin_used = 0;
     CR_TRY(cudaMemsetAsync(h->kf_count, 0, nk * kLevels * sizeof(int), h->stream));
     CR_TRY(cudaStreamSynchronize(h->stream));
@@ -207,17 +228,38 @@ static int stage_h2d(ellc_handle* h, void* dst, const void* src, size_t bytes) {
     void* p = (char*)h->h_pin + h->pin_used;
     std::memcpy(p, src, bytes);
     h->pin_used += aligned;
-    CU_TRY(h, cudaMemcpyAsync(dst, p, bytes, cudaMemcpyHostToDevice, h->stream));
+    // pulled by the SMs, not the copy engine: see pull_host_words_kernel
+    h->launches += launch_pull_host(h->stream, dst, (char*)h->d_pin + ((char*)p - (char*)h->h_pin), bytes);
+    CU_TRY(h, cudaGetLastError());
+    return ELLC_OK;
+}
+
+
+// An upload overwrites a slot on copy_stream.  It must not pass a track batch (compute stream) that still reads the slot:
+// wait for that batch's completion event, unless it is already known to be finished.
+static int guard_slot_write(ellc_handle* h, long long reader_seq) {
+    if (reader_seq <= h->batch_done_seq) return ELLC_OK;
+    if (reader_seq + 4 <= h->batch_seq) { h->batch_done_seq = reader_seq; return ELLC_OK; }   // ring slot recycled => batch finished
+    CU_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->batch_ev[reader_seq & 3], 0));
+    return ELLC_OK;
+}
+static int after_upload(ellc_handle* h) {
+    CU_TRY(h, cudaEventRecord(h->up_ev, h->copy_stream));
+    h->uploads_pending = true;
     return ELLC_OK;
 }
 
 static int ensure_pairs_cap(ellc_handle* h, int n, bool want_trace) {
     if (n > h->pairs_cap) {
-        cudaFree(h->d_pairs); cudaFree(h->d_results); cudaFree(h->d_order);
-        h->d_pairs = nullptr; h->d_results = nullptr; h->d_order = nullptr; h->pairs_cap = 0;
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+        CU_TRY(h, cudaStreamSynchronize(h->d2h_stream));
+        cudaFree(h->d_pairs); cudaFree(h->d_results2[0]); cudaFree(h->d_results2[1]); cudaFree(h->d_order);
+        h->d_pairs = nullptr; h->d_results = h->d_results2[0] = h->d_results2[1] = nullptr; h->d_order = nullptr; h->pairs_cap = 0;
         int cap = n < 256 ? 256 : n;
         CU_TRY(h, cudaMalloc(&h->d_pairs, (size_t)cap * sizeof(ellc_pair)));
-        CU_TRY(h, cudaMalloc(&h->d_results, (size_t)cap * sizeof(ellc_result)));
+        CU_TRY(h, cudaMalloc(&h->d_results2[0], (size_t)cap * sizeof(ellc_result)));
+        CU_TRY(h, cudaMalloc(&h->d_results2[1], (size_t)cap * sizeof(ellc_result)));
+        h->d_results = h->d_results2[0];
         CU_TRY(h, cudaMalloc(&h->d_order, (size_t)cap * sizeof(int)));
         h->pairs_cap = cap;
     }
@@ -259,6 +301,10 @@ static int prepare_keyframes_impl(ellc_handle* h, int n, const int* slots) {
 }
 
 static int flush_dirty(ellc_handle* h) {
+    if (h->uploads_pending) {                              // copy_stream is in order: the last upload's event covers them all
+        CU_TRY(h, cudaStreamWaitEvent(h->stream, h->up_ev, 0));
+        h->uploads_pending = false;
+    }
     if (!h->fr_dirty.empty()) {
         std::vector<int> s;
         for (int v : h->fr_dirty) if (h->fr_state[v] == 1) { s.push_back(v); h->fr_state[v] = 3; }
@@ -345,6 +391,14 @@ static int track_launch(ellc_handle* h, int n, const ellc_pair* pairs, bool want
         if (rc) return rc;
     }
     if (want_trace) CU_TRY(h, cudaMemsetAsync(h->d_trace, 0, (size_t)n * kLevels * ELLC_MAX_TRACE_ITERS * sizeof(ellc_iter_trace), h->stream));
+    // batch bookkeeping: sequence number, result buffer (two alternate, so a finished batch can be downloaded while the
+    // next one runs), completion event (ring of 4: reusing an entry requires its old batch to be finished)
+    const long long seq = h->batch_seq + 1;
+    if (seq > 4 && seq - 4 > h->batch_done_seq) {
+        CU_TRY(h, cudaEventSynchronize(h->batch_ev[seq & 3]));
+        h->batch_done_seq = seq - 4;
+    }
+    h->d_results = h->d_results2[seq & 1];
     TrackParams p;
     fill_params(h, p);
     p.pairs = h->d_pairs; p.order = h->d_order; p.results = h->d_results; p.trace = want_trace ? h->d_trace : nullptr; p.n_pairs = n;
@@ -353,6 +407,9 @@ static int track_launch(ellc_handle* h, int n, const ellc_pair* pairs, bool want
     if (l < 0) { h->err = std::string("track kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()); return ELLC_ERR_CUDA; }
     h->launches += l;
     CU_TRY(h, cudaEventRecord(h->ev1, h->stream));
+    CU_TRY(h, cudaEventRecord(h->batch_ev[seq & 3], h->stream));
+    h->batch_seq = seq;
+    for (int i = 0; i < n; ++i) { h->fr_reader[pairs[i].frame_slot] = seq; h->kf_reader[pairs[i].kf_slot] = seq; }
     CU_TRY(h, cudaGetLastError());
     return ELLC_OK;
 }
@@ -363,11 +420,13 @@ int ellc_upload_frame(ellc_handle* h, int32_t slot, const uint8_t* image) {
     if (!h) return ELLC_ERR_INVALID;
     if (!image || slot < 0 || slot >= h->cfg.max_frames) { h->err = "bad frame slot / null image"; return ELLC_ERR_INVALID; }
     CU_TRY(h, cudaSetDevice(h->cfg.device));
+    int rc = guard_slot_write(h, h->fr_reader[slot]);
+    if (rc) return rc;
     CU_TRY(h, cudaMemcpyAsync(h->fr_img + (int64_t)slot * h->geo.img_off[kLevels], image, (size_t)h->geo.img_off[1],
-                              cudaMemcpyHostToDevice, h->stream));
+                              cudaMemcpyHostToDevice, h->copy_stream));
     h->fr_state[slot] = 1;
     h->fr_dirty.push_back(slot);
-    return ELLC_OK;
+    return after_upload(h);
 }
 
 int ellc_upload_keyframe(ellc_handle* h, int32_t slot, const uint8_t* image, const float* const depth[ELLC_LEVELS],
@@ -376,17 +435,19 @@ int ellc_upload_keyframe(ellc_handle* h, int32_t slot, const uint8_t* image, con
     if (!image || !depth || !var || slot < 0 || slot >= h->cfg.max_keyframes) { h->err = "bad keyframe slot / null pointer"; return ELLC_ERR_INVALID; }
     for (int l = 0; l < kLevels; ++l) if (!depth[l] || !var[l]) { h->err = "null depth/var level"; return ELLC_ERR_INVALID; }
     CU_TRY(h, cudaSetDevice(h->cfg.device));
+    int rc = guard_slot_write(h, h->kf_reader[slot]);
+    if (rc) return rc;
     CU_TRY(h, cudaMemcpyAsync(h->kf_img + (int64_t)slot * h->geo.img_off[kLevels], image, (size_t)h->geo.img_off[1],
-                              cudaMemcpyHostToDevice, h->stream));
+                              cudaMemcpyHostToDevice, h->copy_stream));
     const int64_t win = h->geo.win_off[kLevels];
     for (int l = 0; l < kLevels; ++l) {
         const size_t bytes = (size_t)(h->geo.win_off[l + 1] - h->geo.win_off[l]) * sizeof(float);
-        CU_TRY(h, cudaMemcpyAsync(h->kf_depth + slot * win + h->geo.win_off[l], depth[l], bytes, cudaMemcpyHostToDevice, h->stream));
-        CU_TRY(h, cudaMemcpyAsync(h->kf_var + slot * win + h->geo.win_off[l], var[l], bytes, cudaMemcpyHostToDevice, h->stream));
+        CU_TRY(h, cudaMemcpyAsync(h->kf_depth + slot * win + h->geo.win_off[l], depth[l], bytes, cudaMemcpyHostToDevice, h->copy_stream));
+        CU_TRY(h, cudaMemcpyAsync(h->kf_var + slot * win + h->geo.win_off[l], var[l], bytes, cudaMemcpyHostToDevice, h->copy_stream));
     }
     h->kf_state[slot] = 1;
     h->kf_dirty.push_back(slot);
-    return ELLC_OK;
+    return after_upload(h);
 }
 
 int ellc_frame_image_devptr(ellc_handle* h, int32_t slot, uint8_t** image) {
@@ -423,7 +484,10 @@ int ellc_prepare_keyframes(ellc_handle* h, int32_t n, const int32_t* slots) {
 int ellc_synchronize(ellc_handle* h) {
     if (!h) return ELLC_ERR_INVALID;
     CU_TRY(h, cudaSetDevice(h->cfg.device));
+    CU_TRY(h, cudaStreamSynchronize(h->copy_stream));
     CU_TRY(h, cudaStreamSynchronize(h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->d2h_stream));
+    h->batch_done_seq = h->batch_seq;
     h->pin_used = 0;
     return ELLC_OK;
 }
@@ -437,6 +501,26 @@ int ellc_track_batch_async(ellc_handle* h, int32_t n, const ellc_pair* pairs, co
     return ELLC_OK;
 }
 
+int ellc_results_download(ellc_handle* h, const ellc_result* device_results, int32_t n, ellc_result* results) {
+    if (!h) return ELLC_ERR_INVALID;
+    if (n < 0 || (n > 0 && (!device_results || !results))) { h->err = "bad download arguments"; return ELLC_ERR_INVALID; }
+    if (n == 0) return ELLC_OK;
+    int which = -1;
+    for (int b = 0; b < 2; ++b) if (device_results == h->d_results2[b]) which = b;
+    if (which < 0) { h->err = "pointer was not returned by ellc_track_batch_async"; return ELLC_ERR_INVALID; }
+    CU_TRY(h, cudaSetDevice(h->cfg.device));
+    // the batch that filled this buffer: the most recent sequence number with that parity
+    long long seq = h->batch_seq;
+    if ((seq & 1) != which) seq -= 1;
+    if (seq < 1) { h->err = "no batch has used this buffer yet"; return ELLC_ERR_NOT_READY; }
+    CU_TRY(h, cudaStreamWaitEvent(h->d2h_stream, h->batch_ev[seq & 3], 0));
+    CU_TRY(h, cudaMemcpyAsync(results, device_results, (size_t)n * sizeof(ellc_result), cudaMemcpyDeviceToHost, h->d2h_stream));
+    CU_TRY(h, cudaStreamSynchronize(h->d2h_stream));
+    if (seq > h->batch_done_seq) h->batch_done_seq = seq;
+    if (seq == h->batch_seq) h->pin_used = 0;              // nothing enqueued on the compute stream is still pending
+    return ELLC_OK;
+}
+
 int ellc_track_batch(ellc_handle* h, int32_t n, const ellc_pair* pairs, ellc_result* results, ellc_iter_trace* trace) {
     if (!h) return ELLC_ERR_INVALID;
     if (n < 0 || (n > 0 && (!pairs || !results))) { h->err = "bad pair list / null results"; return ELLC_ERR_INVALID; }
@@ -447,6 +531,7 @@ int ellc_track_batch(ellc_handle* h, int32_t n, const ellc_pair* pairs, ellc_res
     if (trace) CU_TRY(h, cudaMemcpyAsync(trace, h->d_trace, (size_t)n * kLevels * ELLC_MAX_TRACE_ITERS * sizeof(ellc_iter_trace),
                                          cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(h, cudaStreamSynchronize(h->stream));
+    h->batch_done_seq = h->batch_seq;
     h->pin_used = 0;
     return ELLC_OK;
 }
@@ -576,6 +661,10 @@ void ellc_se3_exp(const float pose[6], float T[16]) {
 int64_t ellc_launch_count(const ellc_handle* h) { return h ? h->launches : 0; }
 void ellc_reset_launch_count(ellc_handle* h) { if (h) h->launches = 0; }
 void* ellc_stream(ellc_handle* h) { return h ? (void*)h->stream : nullptr; }
+void* ellc_stream_of(ellc_handle* h, int32_t which) {
+    if (!h) return nullptr;
+    return which == 1 ? (void*)h->copy_stream : which == 2 ? (void*)h->d2h_stream : (void*)h->stream;
+}
 float ellc_last_track_kernel_ms(ellc_handle* h) {
     if (!h || !h->ev_valid) return -1.f;
     float ms = -1.f;

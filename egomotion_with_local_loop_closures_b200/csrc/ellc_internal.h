@@ -14,6 +14,9 @@ int launch_select(cudaStream_t st, const float* depth_pool, const float* var_poo
                   int* rowoff_pool, int* count_pool, SelGeo* geo_pool, SelPix* pix_pool, const LevelK* K,
                   const int* d_slots, int n, const Geometry& geo);
 
+// dst (device, 4-byte aligned, capacity rounded up to 4 bytes) <- pinned host memory read by the SMs (no copy engine)
+int launch_pull_host(cudaStream_t st, void* dst, const void* src_host_devptr, size_t bytes);
+
 // ellc_track.cu
 // Launches the GN tracking kernel for p.n_pairs pairs with `cluster` CTAs per pair.  Returns kernels launched (1) or a
 // negative value on launch-configuration failure (cudaGetLastError carries the reason).

@@ -232,9 +232,25 @@ select_write_kernel(const float* __restrict__ depth_pool, const float* __restric
     }
 }
 
+// Small host payloads (slot lists, pair lists, schedules) are pulled from the pinned staging arena by the SMs instead of
+// the copy engine: a cudaMemcpyAsync on the compute stream would queue in the one H2D engine behind the bulk image /
+// depth uploads of the NEXT batch (copy stream) and stall this batch's kernels for the whole upload burst.
+__global__ void pull_host_words_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src_host, int n_words) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += gridDim.x * blockDim.x) dst[i] = src_host[i];
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // launch wrappers
 // ------------------------------------------------------------------------------------------------------------------
+int launch_pull_host(cudaStream_t st, void* dst, const void* src_host_devptr, size_t bytes) {
+    const int n_words = (int)((bytes + 3) / 4);
+    if (n_words <= 0) return 0;
+    int blocks = (n_words + 255) / 256;
+    if (blocks > 148) blocks = 148;
+    pull_host_words_kernel<<<blocks, 256, 0, st>>>((uint32_t*)dst, (const uint32_t*)src_host_devptr, n_words);
+    return 1;
+}
+
 int launch_pyramid(cudaStream_t st, uint8_t* img_pool, int64_t img_slot_stride, const int* d_slots, int n, const Geometry& geo) {
     int launches = 0;
     for (int l = 1; l < kLevels; ++l) {

@@ -146,8 +146,14 @@ int ellc_prepare_keyframes(ellc_handle* h, int32_t n, const int32_t* kf_slots); 
  * n * ELLC_LEVELS * ELLC_MAX_TRACE_ITERS records indexed [pair][level][iter]. */
 int ellc_track_batch(ellc_handle* h, int32_t n, const ellc_pair* pairs, ellc_result* results, ellc_iter_trace* trace);
 
-/* Same, asynchronous: results stay on the device (pointer valid until the next track call on this handle). */
+/* Same, asynchronous: only enqueues.  Results stay on the device in one of two alternating buffers: the returned pointer
+ * stays valid until the second-next track call on this handle.  Uploads run on their own copy stream, so the uploads of
+ * the next batch overlap this batch's kernels as long as they go to slots this batch does not read (slot reuse is
+ * detected and ordered automatically). */
 int ellc_track_batch_async(ellc_handle* h, int32_t n, const ellc_pair* pairs, const ellc_result** device_results);
+/* Wait for the batch that produced `device_results` and copy its n records to the host (own D2H stream: does not queue
+ * behind batches enqueued later). */
+int ellc_results_download(ellc_handle* h, const ellc_result* device_results, int32_t n, ellc_result* results);
 int ellc_synchronize(ellc_handle* h);
 
 /* One evaluation of the normal equations at a given pose and level WITHOUT updating the pose: the body of
@@ -184,6 +190,8 @@ int64_t ellc_launch_count(const ellc_handle* h);
 void    ellc_reset_launch_count(ellc_handle* h);
 /* cudaStream_t of the handle, as an opaque pointer (for CUDA-event timing on the launching stream) */
 void*   ellc_stream(ellc_handle* h);
+/* which: 0 = compute stream (same as ellc_stream), 1 = H2D upload stream, 2 = D2H result stream (diagnostics). */
+void*   ellc_stream_of(ellc_handle* h, int32_t which);
 /* device time of the track kernel(s) of the most recent ellc_track_batch* call, in milliseconds (CUDA events) */
 float   ellc_last_track_kernel_ms(ellc_handle* h);
 
