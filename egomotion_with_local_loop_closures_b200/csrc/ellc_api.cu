@@ -40,7 +40,7 @@ struct ellc_handle {
     bool ev_valid;
     // pools
     uint8_t* fr_img; uint32_t* fr_tex;
-    uint8_t* kf_img; float* kf_depth; float* kf_var; uint8_t* kf_mask; SelGeo* kf_geo; SelPix* kf_pix;
+    uint8_t* kf_img; float* kf_depth; float* kf_var; uint8_t* kf_mask; SelGeo* kf_geo; SelPix* kf_pix; float* kf_ikf;
     int* kf_count; int* kf_rowcount; int* kf_rowoff;
     std::vector<uint8_t> fr_state, kf_state;          // 0 empty, 1 image present (dirty), 2 prepared
     std::vector<int> fr_dirty, kf_dirty;
@@ -84,10 +84,14 @@ static void build_intrinsics(const ellc_config& c, LevelK K[kLevels]) {
     for (int l = 0; l < kLevels; ++l) {
         const double s = (double)(1 << l);
         K[l].fx = (float)(c.fx / s); K[l].fy = (float)(c.fy / s);
-        K[l].cx = (float)(c.cx / s); K[l].cy = (float)(c.cy / s);
+        K[l].cx = (float)(c.cx / s) + 0.0f; K[l].cy = (float)(c.cy / s) + 0.0f;   // + 0.0f: never -0.0 (bit-pattern bound tests)
         K[l].ifx = 1.0f / K[l].fx; K[l].ify = 1.0f / K[l].fy;
         K[l].fy_ifx = K[l].fy / K[l].fx; K[l].fx_ify = K[l].fx / K[l].fy;
         K[l].cm1 = (float)((c.width >> l) - 1); K[l].rm1 = (float)((c.height >> l) - 1);
+        const float bounds[4] = {(float)(c.width >> l), K[l].cm1, (float)(c.height >> l), K[l].rm1};
+        uint32_t bits[4];
+        std::memcpy(bits, bounds, sizeof(bits));
+        K[l].colsf_bits = bits[0]; K[l].cm1_bits = bits[1]; K[l].rowsf_bits = bits[2]; K[l].rm1_bits = bits[3];
     }
 }
 
@@ -119,7 +123,7 @@ int ellc_destroy(ellc_handle* h) {
     if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
     if (h->d2h_stream) cudaStreamSynchronize(h->d2h_stream);
     cudaFree(h->fr_img); cudaFree(h->fr_tex); cudaFree(h->kf_img); cudaFree(h->kf_depth); cudaFree(h->kf_var);
-    cudaFree(h->kf_mask); cudaFree(h->kf_geo); cudaFree(h->kf_pix); cudaFree(h->kf_count); cudaFree(h->kf_rowcount); cudaFree(h->kf_rowoff);
+    cudaFree(h->kf_mask); cudaFree(h->kf_geo); cudaFree(h->kf_pix); cudaFree(h->kf_ikf); cudaFree(h->kf_count); cudaFree(h->kf_rowcount); cudaFree(h->kf_rowoff);
     cudaFree(h->d_slots); cudaFree(h->d_pairs); cudaFree(h->d_results2[0]); cudaFree(h->d_results2[1]); cudaFree(h->d_order); cudaFree(h->d_trace); cudaFree(h->d_small);
     cudaFree(h->d_weight);
     if (h->h_pin) cudaFreeHost(h->h_pin);
@@ -186,14 +190,17 @@ int ellc_create(const ellc_config* cfg, ellc_handle** out) {
     const int64_t img = h->geo.img_off[kLevels], win = h->geo.win_off[kLevels];
     const int64_t nf = cfg->max_frames, nk = cfg->max_keyframes;
     CR_TRY(cudaMalloc(&h->fr_img, nf * img));
-    CR_TRY(cudaMalloc(&h->fr_tex, nf * (win + kTexPad) * sizeof(uint32_t)));
-    CR_TRY(cudaMemsetAsync(h->fr_tex, 0, nf * (win + kTexPad) * sizeof(uint32_t), h->stream));   // zero texel of every slot
+    CR_TRY(cudaMalloc(&h->fr_tex, (nf * (win + kTexPad) + kTexTail) * sizeof(uint32_t)));
+    CR_TRY(cudaMemsetAsync(h->fr_tex, 0, (nf * (win + kTexPad) + kTexTail) * sizeof(uint32_t), h->stream));   // pack_tex writes the pad words
     CR_TRY(cudaMalloc(&h->kf_img, nk * img));
     CR_TRY(cudaMalloc(&h->kf_depth, nk * win * sizeof(float)));
     CR_TRY(cudaMalloc(&h->kf_var, nk * win * sizeof(float)));
     CR_TRY(cudaMalloc(&h->kf_mask, nk * win));
-    CR_TRY(cudaMalloc(&h->kf_geo, nk * win * sizeof(SelGeo)));
-    CR_TRY(cudaMalloc(&h->kf_pix, nk * win * sizeof(SelPix)));
+    CR_TRY(cudaMalloc(&h->kf_geo, (nk * win + kRecTail) * sizeof(SelGeo)));
+    CR_TRY(cudaMalloc(&h->kf_pix, (nk * win + kRecTail) * sizeof(SelPix)));
+    CR_TRY(cudaMalloc(&h->kf_ikf, (nk * win + kRecTail) * sizeof(float)));
+    CR_TRY(cudaMemsetAsync(h->kf_geo, 0, (nk * win + kRecTail) * sizeof(SelGeo), h->stream));
+    CR_TRY(cudaMemsetAsync(h->kf_ikf, 0, (nk * win + kRecTail) * sizeof(float), h->stream));
     CR_TRY(cudaMalloc(&h->kf_count, nk * kLevels * sizeof(int)));
     CR_TRY(cudaMalloc(&h->kf_rowcount, nk * h->rows_total * sizeof(int)));
     CR_TRY(cudaMalloc(&h->kf_rowoff, nk * h->rows_total * sizeof(int)));
@@ -294,7 +301,7 @@ static int prepare_keyframes_impl(ellc_handle* h, int n, const int* slots) {
     h->launches += launch_pyramid(h->stream, h->kf_img, h->geo.img_off[kLevels], d_slots, n, h->geo);
     h->launches += launch_select(h->stream, h->kf_depth, h->kf_var, h->geo.win_off[kLevels], h->kf_img,
                                  h->geo.img_off[kLevels], h->kf_mask, h->kf_rowcount, h->kf_rowoff, h->kf_count,
-                                 h->kf_geo, h->kf_pix, h->K, d_slots, n, h->geo);
+                                 h->kf_geo, h->kf_pix, h->kf_ikf, h->K, d_slots, n, h->geo);
     CU_TRY(h, cudaGetLastError());
     for (int i = 0; i < n; ++i) h->kf_state[slots[i]] = 2;
     return ELLC_OK;
@@ -334,7 +341,7 @@ static void fill_params(const ellc_handle* h, TrackParams& p) {
     p.stop_threshold = h->cfg.stop_threshold;
     p.jacobian_at_warped = h->cfg.jacobian_at_warped;
     p.tex_pool = h->fr_tex; p.tex_slot_stride = h->geo.win_off[kLevels] + kTexPad;
-    p.geo_pool = h->kf_geo; p.pix_pool = h->kf_pix; p.rec_slot_stride = h->geo.win_off[kLevels];
+    p.geo_pool = h->kf_geo; p.pix_pool = h->kf_pix; p.ikf_pool = h->kf_ikf; p.rec_slot_stride = h->geo.win_off[kLevels];
     p.count_pool = h->kf_count;
     p.level_hi = kLevels - 1; p.level_lo = 0;
 }

@@ -29,19 +29,24 @@ __host__ __device__ inline int selpix_y(SelPix p) { return (int)((p >> 11) & 0x7
 __host__ __device__ inline int selpix_i(SelPix p) { return (int)(p >> 22); }
 
 // Packed texel of the current frame at one pyramid level: everything one bilinear tap needs in one 32-bit word.
-//   bits  0.. 7  intensity I (unsigned)
-//   bits  8..19  2*gradx, 12-bit two's complement  (gradx of src/Frame.cpp:185-285 is a multiple of 0.5 in [-255, 255])
-//   bits 20..31  2*grady, 12-bit two's complement
-// Interpolating the doubled integer gradients and halving the result is bit-identical to interpolating the
-// reference's f32 gradient maps (scaling by 2 is exact in binary floating point).  The all-zero word is an
-// out-of-bounds tap (pixVal = 0, src/Frame.h:211-215).
+//   bits  0.. 9  2*gradx + 512   (gradx of src/Frame.cpp:185-285 is a multiple of 0.5 in [-255, 255])
+//   bits 10..19  2*grady + 512
+//   bits 24..31  intensity I
+// The biased fields sit inside the mantissa range of a float, so the GN kernel turns each of them into an exact float
+// with ONE logic instruction ((t & mask) | magic exponent, PRMT for the intensity byte) instead of shift + mask +
+// int->float conversion.  Interpolating the doubled integer gradients and halving is bit-identical to interpolating the
+// reference's f32 gradient maps (scaling by 2 is exact).  kTexZero is an out-of-bounds tap (pixVal = 0,
+// src/Frame.h:211-215): I = 0, gradx = grady = 0.
 __host__ __device__ inline uint32_t tex_pack(int I, int gx2, int gy2) {
-    return (uint32_t)I | (((uint32_t)gx2 & 0xfffu) << 8) | (((uint32_t)gy2 & 0xfffu) << 20);
+    return (uint32_t)(gx2 + 512) | ((uint32_t)(gy2 + 512) << 10) | ((uint32_t)I << 24);
 }
-constexpr int kTexPad = 4;      // words reserved at the start of every frame slot of the texel pool; word 0 stays zero
-__host__ __device__ inline int tex_I(uint32_t w) { return (int)(w & 0xffu); }
-__host__ __device__ inline int tex_gx2(uint32_t w) { return ((int)(w << 12)) >> 20; }
-__host__ __device__ inline int tex_gy2(uint32_t w) { return ((int)w) >> 20; }
+constexpr uint32_t kTexZero = 512u | (512u << 10);
+constexpr int kTexPad = 4;      // words reserved at the start of every frame slot of the texel pool; they hold kTexZero
+constexpr int kTexTail = 4096;  // mapped words behind the last slot (weight-0 taps may read one row past a level)
+__host__ __device__ inline int tex_I(uint32_t w) { return (int)(w >> 24); }
+__host__ __device__ inline int tex_gx2(uint32_t w) { return (int)(w & 0x3ffu) - 512; }
+__host__ __device__ inline int tex_gy2(uint32_t w) { return (int)((w >> 10) & 0x3ffu) - 512; }
+constexpr int kRecTail = 8192;  // mapped records behind the last keyframe slot (the pixel loop prefetches past a level's end)
 
 // Geometry of the pyramid for one configuration.
 struct Geometry {
@@ -58,6 +63,10 @@ struct LevelK {
     float ifx, ify;            // fast-mode reciprocals
     float fy_ifx, fx_ify;      // fy/fx, fx/fy
     float cm1, rm1;            // float(cols-1), float(rows-1): nCols / nRows of src/Frame.h:196-197
+    // bit patterns of float(cols), float(cols-1), float(rows), float(rows-1): for a projected coordinate u that is not
+    // -0.0, (u >= 0 && floor(u) <= cols-1) == (bits(u) < bits(float(cols))) and (u >= 0 && u <= cols-1) ==
+    // (bits(u) <= bits(float(cols-1))) as unsigned compares (negative and NaN patterns are larger than any bound)
+    uint32_t colsf_bits, cm1_bits, rowsf_bits, rm1_bits;
 };
 
 struct TrackParams {
@@ -73,6 +82,7 @@ struct TrackParams {
     const uint32_t* tex_pool;  int64_t tex_slot_stride;       // packed texels, per frame slot
     const SelGeo* geo_pool;    int64_t rec_slot_stride;       // selection records, per keyframe slot
     const SelPix* pix_pool;
+    const float* ikf_pool;                                    // 2^23 + I_kf per selected pixel (fast flavour)
     const int* count_pool;                                    // [kf_slot][kLevels]
     // work
     const ellc_pair* pairs;

@@ -11,7 +11,7 @@ int launch_pack_tex(cudaStream_t st, const uint8_t* img_pool, int64_t img_slot_s
                     int64_t tex_slot_stride, const int* d_slots, int n, const Geometry& geo);
 int launch_select(cudaStream_t st, const float* depth_pool, const float* var_pool, int64_t win_slot_stride,
                   const uint8_t* img_pool, int64_t img_slot_stride, uint8_t* mask_pool, int* rowcount_pool,
-                  int* rowoff_pool, int* count_pool, SelGeo* geo_pool, SelPix* pix_pool, const LevelK* K,
+                  int* rowoff_pool, int* count_pool, SelGeo* geo_pool, SelPix* pix_pool, float* ikf_pool, const LevelK* K,
                   const int* d_slots, int n, const Geometry& geo);
 
 // dst (device, 4-byte aligned, capacity rounded up to 4 bytes) <- pinned host memory read by the SMs (no copy engine)

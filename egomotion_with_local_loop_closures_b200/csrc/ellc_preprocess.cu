@@ -66,6 +66,7 @@ pack_tex_kernel(const uint8_t* __restrict__ img_pool, int64_t img_slot_stride, u
                 int64_t tex_slot_stride, const int* __restrict__ slots, Geometry geo) {
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= geo.win_off[kLevels]) return;
+    if (gid < kTexPad) tex_pool[(int64_t)slots[blockIdx.y] * tex_slot_stride + gid] = kTexZero;   // the out-of-bounds texel
     int level = 0;
 #pragma unroll
     for (int l = 1; l < kLevels; ++l) level += (gid >= geo.win_off[l]);
@@ -181,7 +182,8 @@ struct KSet { LevelK k[kLevels]; };
 __global__ void __launch_bounds__(SEL_T)
 select_write_kernel(const float* __restrict__ depth_pool, const float* __restrict__ var_pool, int64_t win_slot_stride,
                     const uint8_t* __restrict__ img_pool, int64_t img_slot_stride, const int* __restrict__ rowoff_pool,
-                    int rows_total, SelGeo* __restrict__ geo_pool, SelPix* __restrict__ pix_pool, KSet ks,
+                    int rows_total, SelGeo* __restrict__ geo_pool, SelPix* __restrict__ pix_pool,
+                    float* __restrict__ ikf_pool, KSet ks,
                     const int* __restrict__ slots, Geometry geo) {
     int level, y;
     row_to_level(geo, blockIdx.x, level, y);
@@ -195,6 +197,7 @@ select_write_kernel(const float* __restrict__ depth_pool, const float* __restric
     const int64_t obase = (int64_t)slot * win_slot_stride + geo.win_off[level] + rowoff_pool[(int64_t)slot * rows_total + blockIdx.x];
     SelGeo* __restrict__ og = geo_pool + obase;
     SelPix* __restrict__ op = pix_pool + obase;
+    float* __restrict__ ok = ikf_pool + obase;
     // worldpointY's numerator factor (y - cy) is row-constant
     const float yc = __fsub_rn((float)y, K.cy);
     __shared__ int s_w[SEL_T / 32];
@@ -226,6 +229,7 @@ select_write_kernel(const float* __restrict__ depth_pool, const float* __restric
             const int o = running + wbase + rank_in_warp;
             og[o] = g;
             op[o] = selpix_pack(x, y, img[x]);
+            ok[o] = 8388608.0f + (float)img[x];           // 2^23 + I_kf: same float format as the kernel's intensity taps
         }
         running += total;
         __syncthreads();
@@ -272,7 +276,7 @@ int launch_pack_tex(cudaStream_t st, const uint8_t* img_pool, int64_t img_slot_s
 
 int launch_select(cudaStream_t st, const float* depth_pool, const float* var_pool, int64_t win_slot_stride,
                   const uint8_t* img_pool, int64_t img_slot_stride, uint8_t* mask_pool, int* rowcount_pool,
-                  int* rowoff_pool, int* count_pool, SelGeo* geo_pool, SelPix* pix_pool, const LevelK* K,
+                  int* rowoff_pool, int* count_pool, SelGeo* geo_pool, SelPix* pix_pool, float* ikf_pool, const LevelK* K,
                   const int* d_slots, int n, const Geometry& geo) {
     int rows_total = 0;
     for (int l = 0; l < kLevels; ++l) rows_total += geo.rows[l];
@@ -283,7 +287,7 @@ int launch_select(cudaStream_t st, const float* depth_pool, const float* var_poo
     for (int l = 0; l < kLevels; ++l) ks.k[l] = K[l];
     select_write_kernel<<<dim3(rows_total, n), SEL_T, 0, st>>>(depth_pool, var_pool, win_slot_stride, img_pool,
                                                                 img_slot_stride, rowoff_pool, rows_total, geo_pool,
-                                                                pix_pool, ks, d_slots, geo);
+                                                                pix_pool, ikf_pool, ks, d_slots, geo);
     return 3;
 }
 
