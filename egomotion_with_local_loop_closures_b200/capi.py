@@ -25,7 +25,7 @@ class Config(C.Structure):
                 ("max_iter", C.c_int32 * LEVELS), ("huber_d", C.c_float), ("camera_pixel_noise_2", C.c_float),
                 ("weight", C.c_float * 6), ("stop_threshold", C.c_float), ("arithmetic", C.c_int32),
                 ("jacobian_at_warped", C.c_int32), ("max_keyframes", C.c_int32), ("max_frames", C.c_int32),
-                ("ctas_per_pair", C.c_int32), ("device", C.c_int32)]
+                ("ctas_per_pair", C.c_int32), ("device", C.c_int32), ("pairs_per_cta", C.c_int32)]
 
 
 class Pair(C.Structure):

@@ -12,6 +12,7 @@
 // the next consumer (track, evaluate, read-back) -- a whole batch costs 4 (frames) + 6 (keyframes) launches.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -344,6 +345,7 @@ static void fill_params(const ellc_handle* h, TrackParams& p) {
     p.geo_pool = h->kf_geo; p.pix_pool = h->kf_pix; p.ikf_pool = h->kf_ikf; p.rec_slot_stride = h->geo.win_off[kLevels];
     p.count_pool = h->kf_count;
     p.level_hi = kLevels - 1; p.level_lo = 0;
+    p.pairs_per_cta = 1;
 }
 
 static int pick_cluster(const ellc_handle* h, int n) {
@@ -353,6 +355,16 @@ static int pick_cluster(const ellc_handle* h, int n) {
     c = 8;
     while (c > 1 && (int64_t)n * c > 296) c >>= 1;
     return c;
+}
+
+// Pairs per CTA (lockstep slots): with enough pairs to fill the GPU several times over, two pairs per CTA overlap their
+// serial solves; small batches keep one pair per CTA so that every SM gets work.
+static int pick_pairs_per_cta(const ellc_handle* h, int n, int cluster) {
+    if (cluster != 1) return 1;
+    int np = h->cfg.pairs_per_cta;
+    if (const char* e = std::getenv("ELLC_PAIRS_PER_CTA")) np = std::atoi(e);
+    if (np >= 1 && np <= 4) return np;
+    return 1;                                              // measured: 2 is within noise of 1 (the other CTA of the SM already fills the solve gap)
 }
 
 static int validate_pairs(ellc_handle* h, int n, const ellc_pair* pairs) {
@@ -410,7 +422,13 @@ static int track_launch(ellc_handle* h, int n, const ellc_pair* pairs, bool want
     fill_params(h, p);
     p.pairs = h->d_pairs; p.order = h->d_order; p.results = h->d_results; p.trace = want_trace ? h->d_trace : nullptr; p.n_pairs = n;
     CU_TRY(h, cudaEventRecord(h->ev0, h->stream));
-    const int l = launch_track(h->stream, p, pick_cluster(h, n), h->cfg.arithmetic == ELLC_ARITH_STRICT);
+    const int cluster = pick_cluster(h, n);
+    p.pairs_per_cta = pick_pairs_per_cta(h, n, cluster);
+    // diagnostics (tools/gpu_solve_cost.sh): fixed iteration counts with / without the solve
+    if (const char* e = std::getenv("ELLC_DEBUG_NO_UPDATE")) if (*e == '1') p.no_update = 1;
+    if (const char* e = std::getenv("ELLC_DEBUG_MAX_ITER")) std::sscanf(e, "%d,%d,%d,%d", &p.max_iter[0], &p.max_iter[1], &p.max_iter[2], &p.max_iter[3]);
+    if (const char* e = std::getenv("ELLC_DEBUG_NO_STOP")) if (*e == '1') p.stop_threshold = -1.0f;
+    const int l = launch_track(h->stream, p, cluster, h->cfg.arithmetic == ELLC_ARITH_STRICT);
     if (l < 0) { h->err = std::string("track kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()); return ELLC_ERR_CUDA; }
     h->launches += l;
     CU_TRY(h, cudaEventRecord(h->ev1, h->stream));

@@ -90,6 +90,7 @@ struct TrackParams {
     ellc_result* results;
     ellc_iter_trace* trace;    // optional [pair][level][ELLC_MAX_TRACE_ITERS]
     int n_pairs;
+    int pairs_per_cta;         // pairs tracked in lockstep by one CTA (1..4); clusters always track one
     // evaluate-only mode (ellc_gn_evaluate): run `level_hi..level_lo`, `iter_limit` iterations, no pose update
     int level_hi, level_lo;
     int iter_limit;            // 0 = use max_iter

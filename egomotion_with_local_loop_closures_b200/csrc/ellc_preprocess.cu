@@ -57,6 +57,59 @@ pyrdown_u8_kernel(uint8_t* __restrict__ pool, int64_t slot_stride, const int* __
     }
 }
 
+// Word-wide form of K1 for source widths that are a multiple of 8 (all BASELINE sizes).  One thread produces a strip of
+// 4 (x) by PDV_R (y) output pixels: per source row it loads 4 aligned words (its 8 bytes plus the neighbours' halo), forms
+// the four horizontal [1 4 6 4 1] sums in registers, and keeps a five-row sliding window of them for the vertical pass;
+// adjacent threads own adjacent output quads, so loads and the 4-byte stores are coalesced.  Same exact integer result.
+constexpr int PDV_R = 8;
+__device__ __forceinline__ void pdv_hrow(const uint8_t* __restrict__ row, int cq, int last_cq, int (&h)[4]) {
+    const uint2 ab = *reinterpret_cast<const uint2*>(row + 8 * cq);
+    uint32_t l, r;
+    if (cq == 0) l = __byte_perm(ab.x, 0, 0x1200);               // reflect-101: bytes -2, -1 = bytes 2, 1 (placed at positions 2, 3)
+    else l = *reinterpret_cast<const uint32_t*>(row + 8 * cq - 4);
+    if (cq == last_cq) r = __byte_perm(ab.y, 0, 0x4012);         // bytes w, w+1, w+2 = bytes w-2, w-3, w-4
+    else r = *reinterpret_cast<const uint32_t*>(row + 8 * cq + 8);
+    int sb[13];
+    sb[0] = (l >> 16) & 0xff; sb[1] = l >> 24;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { sb[2 + i] = (ab.x >> (8 * i)) & 0xff; sb[6 + i] = (ab.y >> (8 * i)) & 0xff; }
+    sb[10] = r & 0xff; sb[11] = (r >> 8) & 0xff; sb[12] = (r >> 16) & 0xff;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) h[j] = sb[2 * j] + 4 * sb[2 * j + 1] + 6 * sb[2 * j + 2] + 4 * sb[2 * j + 3] + sb[2 * j + 4];
+}
+
+__global__ void __launch_bounds__(128)
+pyrdown_u8_vec_kernel(uint8_t* __restrict__ pool, int64_t slot_stride, const int* __restrict__ slots,
+                      int64_t src_off, int sw, int sh, int64_t dst_off, int dw, int dh) {
+    const int dwq = dw >> 2;                                     // output quads per row
+    const int item = blockIdx.x * blockDim.x + threadIdx.x;
+    const int strips = (dh + PDV_R - 1) / PDV_R;
+    if (item >= dwq * strips) return;
+    const int cq = item % dwq, y0 = (item / dwq) * PDV_R;
+    uint8_t* base = pool + (int64_t)slots[blockIdx.y] * slot_stride;
+    const uint8_t* __restrict__ src = base + src_off;
+    uint8_t* __restrict__ dst = base + dst_off;
+    int h[5][4];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) pdv_hrow(src + (int64_t)reflect101(2 * y0 - 2 + k, sh) * sw, cq, dwq - 1, h[k]);
+#pragma unroll
+    for (int i = 0; i < PDV_R; ++i) {
+        const int y = y0 + i;
+        if (y >= dh) break;
+        pdv_hrow(src + (int64_t)reflect101(2 * y + 1, sh) * sw, cq, dwq - 1, h[3]);
+        pdv_hrow(src + (int64_t)reflect101(2 * y + 2, sh) * sw, cq, dwq - 1, h[4]);
+        uint32_t o = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int acc = h[0][j] + 4 * h[1][j] + 6 * h[2][j] + 4 * h[3][j] + h[4][j];
+            o |= (uint32_t)((acc + 128) >> 8) << (8 * j);
+        }
+        *reinterpret_cast<uint32_t*>(dst + (int64_t)y * dw + 4 * cq) = o;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { h[0][j] = h[2][j]; h[1][j] = h[3][j]; h[2][j] = h[4][j]; }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // K2: packed texels for all levels of a batch of frame slots.  One thread per pixel of the concatenated level windows.
 // Border rule of src/Frame.cpp:222-283: one-sided, un-halved differences on the 1-px border of the (cols x rows) window.
@@ -85,6 +138,50 @@ pack_tex_kernel(const uint8_t* __restrict__ img_pool, int64_t img_slot_stride, u
     else if (y == rows - 1) gy2 = 2 * (c - (int)r[x - stride]);
     else gy2 = (int)r[stride + x] - (int)r[x - stride];
     tex_pool[(int64_t)slot * tex_slot_stride + kTexPad + gid] = tex_pack(c, gx2, gy2);
+}
+
+// Vector form for pyramids whose every level has a multiple-of-4 width (all BASELINE sizes): one thread packs four
+// consecutive texels -- three 32-bit row loads plus two neighbour bytes in, one 16-byte store out -- so the kernel streams
+// at HBM speed (P bytes in, 4 P bytes out per frame) instead of issuing five byte loads per texel.
+__global__ void __launch_bounds__(256)
+pack_tex_vec4_kernel(const uint8_t* __restrict__ img_pool, int64_t img_slot_stride, uint32_t* __restrict__ tex_pool,
+                     int64_t tex_slot_stride, const int* __restrict__ slots, Geometry geo) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;          // quad index over the concatenated windows
+    if (q * 4 >= geo.win_off[kLevels]) return;
+    const int slot = slots[blockIdx.y];
+    uint32_t* __restrict__ tex = tex_pool + (int64_t)slot * tex_slot_stride;
+    if (q == 0) *reinterpret_cast<uint4*>(tex) = make_uint4(kTexZero, kTexZero, kTexZero, kTexZero);   // the out-of-bounds texel
+    const int64_t gid = q * 4;
+    int level = 0;
+#pragma unroll
+    for (int l = 1; l < kLevels; ++l) level += (gid >= geo.win_off[l]);
+    const int cols = geo.cols[level], rows = geo.rows[level], stride = geo.pyr_w[level];
+    const int local = (int)(gid - geo.win_off[level]);
+    const int y = local / cols, x0 = local - y * cols;
+    const uint8_t* __restrict__ r = img_pool + (int64_t)slot * img_slot_stride + geo.img_off[level] + (int64_t)y * stride;
+    const uint32_t cw = *reinterpret_cast<const uint32_t*>(r + x0);
+    const bool top = (y == 0), bot = (y == rows - 1);
+    const uint32_t uw = *reinterpret_cast<const uint32_t*>(r + x0 - (top ? 0 : stride));
+    const uint32_t dw = *reinterpret_cast<const uint32_t*>(r + x0 + (bot ? 0 : stride));
+    int c[6];                                               // I[x0-1 .. x0+4]
+    c[1] = cw & 0xff; c[2] = (cw >> 8) & 0xff; c[3] = (cw >> 16) & 0xff; c[4] = cw >> 24;
+    c[0] = (x0 > 0) ? r[x0 - 1] : 0;
+    c[5] = (x0 + 4 < cols) ? r[x0 + 4] : 0;
+    uint32_t out[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int x = x0 + i, ci = c[i + 1];
+        const int up = (uw >> (8 * i)) & 0xff, dn = (dw >> (8 * i)) & 0xff;
+        int gx2, gy2;
+        if (x == 0) gx2 = 2 * (c[i + 2] - ci);
+        else if (x == cols - 1) gx2 = 2 * (ci - c[i]);
+        else gx2 = c[i + 2] - c[i];
+        if (top) gy2 = 2 * (dn - ci);
+        else if (bot) gy2 = 2 * (ci - up);
+        else gy2 = dn - up;
+        out[i] = tex_pack(ci, gx2, gy2);
+    }
+    *reinterpret_cast<uint4*>(tex + kTexPad + gid) = make_uint4(out[0], out[1], out[2], out[3]);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -258,10 +355,16 @@ int launch_pull_host(cudaStream_t st, void* dst, const void* src_host_devptr, si
 int launch_pyramid(cudaStream_t st, uint8_t* img_pool, int64_t img_slot_stride, const int* d_slots, int n, const Geometry& geo) {
     int launches = 0;
     for (int l = 1; l < kLevels; ++l) {
-        dim3 grid((geo.pyr_w[l] + PD_TX - 1) / PD_TX, (geo.pyr_h[l] + PD_TY - 1) / PD_TY, n);
-        pyrdown_u8_kernel<<<grid, dim3(PD_TX, PD_TY), 0, st>>>(img_pool, img_slot_stride, d_slots, geo.img_off[l - 1],
-                                                               geo.pyr_w[l - 1], geo.pyr_h[l - 1], geo.img_off[l],
-                                                               geo.pyr_w[l], geo.pyr_h[l]);
+        const int sw = geo.pyr_w[l - 1], sh = geo.pyr_h[l - 1], dw = geo.pyr_w[l], dh = geo.pyr_h[l];
+        if (sw % 8 == 0 && sw >= 16 && sh >= 2 && img_slot_stride % 8 == 0 && geo.img_off[l - 1] % 8 == 0 && geo.img_off[l] % 4 == 0) {
+            const int items = (dw / 4) * ((dh + PDV_R - 1) / PDV_R);
+            pyrdown_u8_vec_kernel<<<dim3((items + 127) / 128, n), 128, 0, st>>>(img_pool, img_slot_stride, d_slots, geo.img_off[l - 1],
+                                                                                sw, sh, geo.img_off[l], dw, dh);
+        } else {
+            dim3 grid((dw + PD_TX - 1) / PD_TX, (dh + PD_TY - 1) / PD_TY, n);
+            pyrdown_u8_kernel<<<grid, dim3(PD_TX, PD_TY), 0, st>>>(img_pool, img_slot_stride, d_slots, geo.img_off[l - 1],
+                                                                   sw, sh, geo.img_off[l], dw, dh);
+        }
         ++launches;
     }
     return launches;
@@ -269,8 +372,16 @@ int launch_pyramid(cudaStream_t st, uint8_t* img_pool, int64_t img_slot_stride, 
 
 int launch_pack_tex(cudaStream_t st, const uint8_t* img_pool, int64_t img_slot_stride, uint32_t* tex_pool,
                     int64_t tex_slot_stride, const int* d_slots, int n, const Geometry& geo) {
-    dim3 grid((unsigned)((geo.win_off[kLevels] + 255) / 256), n);
-    pack_tex_kernel<<<grid, 256, 0, st>>>(img_pool, img_slot_stride, tex_pool, tex_slot_stride, d_slots, geo);
+    bool vec = (img_slot_stride % 4 == 0) && (tex_slot_stride % 4 == 0);
+    for (int l = 0; l < kLevels; ++l)
+        vec = vec && (geo.cols[l] % 4 == 0) && (geo.pyr_w[l] % 4 == 0) && (geo.img_off[l] % 4 == 0) && (geo.win_off[l] % 4 == 0);
+    if (vec) {
+        dim3 grid((unsigned)((geo.win_off[kLevels] / 4 + 255) / 256), n);
+        pack_tex_vec4_kernel<<<grid, 256, 0, st>>>(img_pool, img_slot_stride, tex_pool, tex_slot_stride, d_slots, geo);
+    } else {
+        dim3 grid((unsigned)((geo.win_off[kLevels] + 255) / 256), n);
+        pack_tex_kernel<<<grid, 256, 0, st>>>(img_pool, img_slot_stride, tex_pool, tex_slot_stride, d_slots, geo);
+    }
     return 1;
 }
 

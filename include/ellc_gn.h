@@ -66,6 +66,8 @@ typedef struct ellc_config {
     int32_t max_frames;               /* frame slots resident on the device                                       */
     int32_t ctas_per_pair;            /* thread-block cluster size per pair: 1,2,4,8; 0 = choose from batch size  */
     int32_t device;                   /* CUDA device ordinal                                                      */
+    int32_t pairs_per_cta;            /* pairs one CTA tracks in lockstep (their serial solves overlap): 1..4;
+                                         0 = choose from batch size.  Only used when ctas_per_pair resolves to 1  */
 } ellc_config;
 
 /* One frame-keyframe pair = one call of GetImagePoseEstimate (src/ImageFunc.h:31). */
