@@ -166,7 +166,7 @@ def run_reference(args, rank, world):
         return
     import oracle
     cores = os.cpu_count() or 1
-    n_pairs = max(cores * 24, 48)
+    n_pairs = max(cores * 64, 256)                        # ~3 s of CPU work per step
     n_frames = max(8, n_pairs // args.pairs_per_frame)
     wl = build_workload(min(args.keyframes, 8), n_frames, args.pairs_per_frame, seed=0)
     n_pairs = min(n_pairs, len(wl["kf_idx"]))
@@ -375,7 +375,18 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = alg / (k_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    # DRAM traffic of the dominant kernel: one `ncu --set full` capture of this command (profiles/r01_traffic.json, made by
+    # tools/profile_summary.py), bytes per launch like the algorithmic figure; scaled by pair count if the workload differs.
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) * n_pairs / tj["pairs_per_launch"]
+        traffic_src = "profiles/r01_traffic.json (%s; dram__bytes_read + write of one launch of %d pairs%s)" % (
+            tj["report"], tj["pairs_per_launch"], "" if n_pairs == tj["pairs_per_launch"] else ", scaled by pair count")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_unit": "bytes per launch (compare with algorithmic_bytes_per_launch)", "traffic_source": traffic_src,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                 "kernel": "gn_track_kernel", "kernel_ms_per_launch": k_ms, "algorithmic_bytes_per_launch": alg,
                 "kernel_share_of_step": k_ms / (ms / args.steps),
@@ -396,7 +407,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import oracle
         cores = os.cpu_count() or 1
-        ns = min(n_pairs, max(cores * 4, 16))
+        ns = min(n_pairs, max(cores * 256, 1024))           # ~10-15 s of CPU work on the box's cores
         ocfg = oracle.default_config(W, H, fx=float(k["fx"]), fy=float(k["fy"]), cx=float(k["cx"]), cy=float(k["cy"]))
         oposes, secs = oracle.track_many(ocfg, wl["kf_idx"][:ns], wl["fr_idx"][:ns], wl["kf_images"], wl["frames"], wl["kf_depth"],
                                          wl["kf_var"], wl["init"][:ns], n_workers=cores)

@@ -64,7 +64,7 @@ SYMBOLS = ["ellc_default_config", "ellc_create", "ellc_destroy", "ellc_last_erro
            "ellc_results_download",
            "ellc_synchronize", "ellc_gn_evaluate", "ellc_solve_update", "ellc_read_frame_level",
            "ellc_read_keyframe_level", "ellc_level_dims", "ellc_concat_relative", "ellc_concat_origin",
-           "ellc_se3_exp", "ellc_launch_count", "ellc_reset_launch_count", "ellc_stream", "ellc_stream_of", "ellc_last_track_kernel_ms"]
+           "ellc_se3_exp", "ellc_launch_count", "ellc_reset_launch_count", "ellc_stream", "ellc_stream_of", "ellc_selftest_division", "ellc_last_track_kernel_ms"]
 
 _lib = None
 
@@ -106,6 +106,7 @@ def lib():
         L.ellc_reset_launch_count.argtypes = [C.c_void_p]
         L.ellc_stream.restype = C.c_void_p
         L.ellc_stream.argtypes = [C.c_void_p]
+        L.ellc_selftest_division.argtypes = [C.c_void_p, C.c_int64, C.c_uint64, C.POINTER(C.c_int64)]
         L.ellc_stream_of.restype = C.c_void_p
         L.ellc_stream_of.argtypes = [C.c_void_p, C.c_int32]
         L.ellc_last_track_kernel_ms.restype = C.c_float
@@ -295,6 +296,11 @@ class Tracker:
 
     def stream(self):
         return lib().ellc_stream(self._h)
+
+    def selftest_division(self, n, seed=1):
+        out = (C.c_int64 * 2)()
+        self._chk(lib().ellc_selftest_division(self._h, int(n), int(seed), out))
+        return int(out[0]), int(out[1])
 
     def stream_of(self, which):
         return lib().ellc_stream_of(self._h, which)

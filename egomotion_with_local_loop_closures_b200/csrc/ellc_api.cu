@@ -686,6 +686,19 @@ void ellc_se3_exp(const float pose[6], float T[16]) {
 int64_t ellc_launch_count(const ellc_handle* h) { return h ? h->launches : 0; }
 void ellc_reset_launch_count(ellc_handle* h) { if (h) h->launches = 0; }
 void* ellc_stream(ellc_handle* h) { return h ? (void*)h->stream : nullptr; }
+int ellc_selftest_division(ellc_handle* h, int64_t n, uint64_t seed, int64_t mismatches[2]) {
+    if (!h) return ELLC_ERR_INVALID;
+    if (n < 0 || !mismatches) { h->err = "bad self-test arguments"; return ELLC_ERR_INVALID; }
+    CU_TRY(h, cudaSetDevice(h->cfg.device));
+    unsigned long long* d = reinterpret_cast<unsigned long long*>(h->d_small);
+    CU_TRY(h, cudaMemsetAsync(d, 0, 2 * sizeof(unsigned long long), h->stream));
+    h->launches += launch_div_selftest(h->stream, (long long)n, (unsigned long long)seed, d);
+    unsigned long long out[2] = {0, 0};
+    CU_TRY(h, cudaMemcpyAsync(out, d, sizeof(out), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    mismatches[0] = (int64_t)out[0]; mismatches[1] = (int64_t)out[1];
+    return ELLC_OK;
+}
 void* ellc_stream_of(ellc_handle* h, int32_t which) {
     if (!h) return nullptr;
     return which == 1 ? (void*)h->copy_stream : which == 2 ? (void*)h->d2h_stream : (void*)h->stream;

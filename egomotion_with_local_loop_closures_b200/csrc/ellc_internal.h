@@ -22,6 +22,8 @@ int launch_pull_host(cudaStream_t st, void* dst, const void* src_host_devptr, si
 // negative value on launch-configuration failure (cudaGetLastError carries the reason).
 int launch_track(cudaStream_t st, const TrackParams& p, int cluster, bool strict);
 // single-thread kernel running solve_update_f on the device (ellc_solve_update)
+// div2_rn_shared (the pixel loop's shared-reciprocal exact division) against __fdiv_rn on n pseudo-random operand triples
+int launch_div_selftest(cudaStream_t st, long long n, unsigned long long seed, unsigned long long* d_counts /*[2]*/);
 int launch_solve_update(cudaStream_t st, const float* d_in /*H36 b6 pose6 weight6*/, float* d_out /*pose6 delta6 wp1 ok1*/);
 
 }  // namespace ellc

@@ -192,6 +192,10 @@ int64_t ellc_launch_count(const ellc_handle* h);
 void    ellc_reset_launch_count(ellc_handle* h);
 /* cudaStream_t of the handle, as an opaque pointer (for CUDA-event timing on the launching stream) */
 void*   ellc_stream(ellc_handle* h);
+/* Self-test of the GN kernel's shared-reciprocal division (the hand-run div.rn fast path that yields both X'/Z' and Y'/Z' of
+ * src/PixelWisePyramid.cpp:250-251) against __fdiv_rn on n pseudo-random operand triples; mismatches[0]: quotients with a normal
+ * result that differ, mismatches[1]: differing quotients below 2^-120. */
+int ellc_selftest_division(ellc_handle* h, int64_t n, uint64_t seed, int64_t mismatches[2]);
 /* which: 0 = compute stream (same as ellc_stream), 1 = H2D upload stream, 2 = D2H result stream (diagnostics). */
 void*   ellc_stream_of(ellc_handle* h, int32_t which);
 /* device time of the track kernel(s) of the most recent ellc_track_batch* call, in milliseconds (CUDA events) */
