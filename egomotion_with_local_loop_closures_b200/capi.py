@@ -12,6 +12,7 @@ import numpy as np
 LEVELS = 4
 MAX_TRACE_ITERS = 16
 ARITH_FAST, ARITH_STRICT = 0, 1
+PAIR_DEFAULT, PAIR_CONST_WEIGHT, PAIR_SAVE_WEIGHTS = 0, 1, 2
 _LIB_PATH = os.environ.get("ELLC_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libellc_gn.so")
 
 
@@ -64,7 +65,9 @@ SYMBOLS = ["ellc_default_config", "ellc_create", "ellc_destroy", "ellc_last_erro
            "ellc_results_download",
            "ellc_synchronize", "ellc_gn_evaluate", "ellc_solve_update", "ellc_read_frame_level",
            "ellc_read_keyframe_level", "ellc_level_dims", "ellc_concat_relative", "ellc_concat_origin",
-           "ellc_se3_exp", "ellc_launch_count", "ellc_reset_launch_count", "ellc_stream", "ellc_stream_of", "ellc_selftest_division", "ellc_last_track_kernel_ms"]
+           "ellc_se3_exp", "ellc_launch_count", "ellc_reset_launch_count", "ellc_stream", "ellc_stream_of", "ellc_selftest_division", "ellc_reset_keyframe_weights", "ellc_accumulate_weights",
+           "ellc_finalise_weights", "ellc_upload_keyframe_weights", "ellc_read_keyframe_weights", "ellc_read_frame_weights",
+           "ellc_prepare_keyframes_lc", "ellc_last_track_kernel_ms"]
 
 _lib = None
 
@@ -106,6 +109,13 @@ def lib():
         L.ellc_reset_launch_count.argtypes = [C.c_void_p]
         L.ellc_stream.restype = C.c_void_p
         L.ellc_stream.argtypes = [C.c_void_p]
+        L.ellc_reset_keyframe_weights.argtypes = [C.c_void_p, C.c_int32]
+        L.ellc_accumulate_weights.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+        L.ellc_finalise_weights.argtypes = [C.c_void_p, C.c_int32]
+        L.ellc_upload_keyframe_weights.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+        L.ellc_read_keyframe_weights.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_int32)]
+        L.ellc_read_frame_weights.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+        L.ellc_prepare_keyframes_lc.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.ellc_selftest_division.argtypes = [C.c_void_p, C.c_int64, C.c_uint64, C.POINTER(C.c_int64)]
         L.ellc_stream_of.restype = C.c_void_p
         L.ellc_stream_of.argtypes = [C.c_void_p, C.c_int32]
@@ -296,6 +306,38 @@ class Tracker:
 
     def stream(self):
         return lib().ellc_stream(self._h)
+
+    # -- constant-weight loop-closure variant
+    def reset_keyframe_weights(self, kf_slot):
+        self._chk(lib().ellc_reset_keyframe_weights(self._h, kf_slot))
+
+    def accumulate_weights(self, kf_slot, frame_slots):
+        fs = np.ascontiguousarray(frame_slots, np.int32)
+        self._chk(lib().ellc_accumulate_weights(self._h, kf_slot, len(fs), _p(fs)))
+
+    def finalise_weights(self, kf_slot):
+        self._chk(lib().ellc_finalise_weights(self._h, kf_slot))
+
+    def upload_keyframe_weights(self, kf_slot, weights, counts=None):
+        keep = [np.ascontiguousarray(w, np.float32) for w in weights]
+        ptrs = (C.c_void_p * 4)(*[_p(w) for w in keep])
+        cnt = np.ascontiguousarray(counts, np.int32) if counts is not None else None
+        self._chk(lib().ellc_upload_keyframe_weights(self._h, kf_slot, ptrs, _p(cnt) if cnt is not None else None))
+
+    def read_keyframe_weights(self, kf_slot, level):
+        out = np.zeros((self.cfg.height >> level, self.cfg.width >> level), np.float32)
+        cnt = C.c_int32()
+        self._chk(lib().ellc_read_keyframe_weights(self._h, kf_slot, level, _p(out), C.byref(cnt)))
+        return out, cnt.value
+
+    def read_frame_weights(self, frame_slot, level):
+        out = np.zeros((self.cfg.height >> level, self.cfg.width >> level), np.float32)
+        self._chk(lib().ellc_read_frame_weights(self._h, frame_slot, level, _p(out)))
+        return out
+
+    def prepare_keyframes_lc(self, kf_slots):
+        ks = np.ascontiguousarray(kf_slots, np.int32)
+        self._chk(lib().ellc_prepare_keyframes_lc(self._h, len(ks), _p(ks)))
 
     def selftest_division(self, n, seed=1):
         out = (C.c_int64 * 2)()

@@ -42,6 +42,10 @@ struct ellc_handle {
     // pools
     uint8_t* fr_img; uint32_t* fr_tex;
     uint8_t* kf_img; float* kf_depth; float* kf_var; uint8_t* kf_mask; SelGeo* kf_geo; SelPix* kf_pix; float* kf_ikf;
+    // loop-closure state, allocated on first use (ensure_lc_pools)
+    float* fr_weight; float* kf_weight; LcRec* kf_lc; float* kf_lcH;
+    std::vector<int> kf_wcount;                        // numWeightsAdded[level] per keyframe slot
+    std::vector<char> kf_lc_ready;                     // LcRec / hessian built for the slot's current contents
     int* kf_count; int* kf_rowcount; int* kf_rowoff;
     std::vector<uint8_t> fr_state, kf_state;          // 0 empty, 1 image present (dirty), 2 prepared
     std::vector<int> fr_dirty, kf_dirty;
@@ -124,7 +128,8 @@ int ellc_destroy(ellc_handle* h) {
     if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
     if (h->d2h_stream) cudaStreamSynchronize(h->d2h_stream);
     cudaFree(h->fr_img); cudaFree(h->fr_tex); cudaFree(h->kf_img); cudaFree(h->kf_depth); cudaFree(h->kf_var);
-    cudaFree(h->kf_mask); cudaFree(h->kf_geo); cudaFree(h->kf_pix); cudaFree(h->kf_ikf); cudaFree(h->kf_count); cudaFree(h->kf_rowcount); cudaFree(h->kf_rowoff);
+    cudaFree(h->kf_mask); cudaFree(h->kf_geo); cudaFree(h->kf_pix); cudaFree(h->kf_ikf);
+    cudaFree(h->fr_weight); cudaFree(h->kf_weight); cudaFree(h->kf_lc); cudaFree(h->kf_lcH); cudaFree(h->kf_count); cudaFree(h->kf_rowcount); cudaFree(h->kf_rowoff);
     cudaFree(h->d_slots); cudaFree(h->d_pairs); cudaFree(h->d_results2[0]); cudaFree(h->d_results2[1]); cudaFree(h->d_order); cudaFree(h->d_trace); cudaFree(h->d_small);
     cudaFree(h->d_weight);
     if (h->h_pin) cudaFreeHost(h->h_pin);
@@ -187,6 +192,8 @@ int ellc_create(const ellc_config* cfg, ellc_handle** out) {
     for (int i = 0; i < 4; ++i) CR_TRY(cudaEventCreateWithFlags(&h->batch_ev[i], cudaEventDisableTiming));
     h->ev_valid = true;
     h->fr_reader.assign(cfg->max_frames, 0);
+    h->kf_wcount.assign((size_t)cfg->max_keyframes * kLevels, 0);
+    h->kf_lc_ready.assign(cfg->max_keyframes, 0);
     h->kf_reader.assign(cfg->max_keyframes, 0);
     const int64_t img = h->geo.img_off[kLevels], win = h->geo.win_off[kLevels];
     const int64_t nf = cfg->max_frames, nk = cfg->max_keyframes;
@@ -332,6 +339,22 @@ static int flush_dirty(ellc_handle* h) {
     return ELLC_OK;
 }
 
+// Pools of the constant-weight loop-closure path: frame weight images (display_weightimg of ELLC_PAIR_SAVE_WEIGHTS tracks),
+// keyframe weight pyramids, loop-closure records and hessians.  ~3 x the selection-list memory, so only on first use.
+static int ensure_lc_pools(ellc_handle* h) {
+    if (h->kf_weight) return ELLC_OK;
+    const int64_t win = h->geo.win_off[kLevels];
+    const int64_t nf = h->cfg.max_frames, nk = h->cfg.max_keyframes;
+    CU_TRY(h, cudaMalloc(&h->fr_weight, (size_t)(nf * win) * sizeof(float)));
+    CU_TRY(h, cudaMalloc(&h->kf_lc, (size_t)(nk * win + kRecTail) * sizeof(LcRec)));
+    CU_TRY(h, cudaMalloc(&h->kf_lcH, (size_t)nk * kLevels * 36 * sizeof(float)));
+    CU_TRY(h, cudaMalloc(&h->kf_weight, (size_t)(nk * win) * sizeof(float)));
+    CU_TRY(h, cudaMemsetAsync(h->fr_weight, 0, (size_t)(nf * win) * sizeof(float), h->stream));
+    CU_TRY(h, cudaMemsetAsync(h->kf_weight, 0, (size_t)(nk * win) * sizeof(float), h->stream));     // Mat::zeros, src/Frame.cpp:114-117
+    CU_TRY(h, cudaMemsetAsync(h->kf_lc, 0, (size_t)(nk * win + kRecTail) * sizeof(LcRec), h->stream));
+    return ELLC_OK;
+}
+
 static void fill_params(const ellc_handle* h, TrackParams& p) {
     std::memset(&p, 0, sizeof(p));
     p.geo = h->geo;
@@ -344,6 +367,7 @@ static void fill_params(const ellc_handle* h, TrackParams& p) {
     p.tex_pool = h->fr_tex; p.tex_slot_stride = h->geo.win_off[kLevels] + kTexPad;
     p.geo_pool = h->kf_geo; p.pix_pool = h->kf_pix; p.ikf_pool = h->kf_ikf; p.rec_slot_stride = h->geo.win_off[kLevels];
     p.count_pool = h->kf_count;
+    p.frw_pool = h->fr_weight; p.lc_pool = h->kf_lc; p.lc_H = h->kf_lcH;
     p.level_hi = kLevels - 1; p.level_lo = 0;
     p.pairs_per_cta = 1;
 }
@@ -378,9 +402,13 @@ static int validate_pairs(ellc_handle* h, int n, const ellc_pair* pairs) {
             h->err = "pair references a slot that was never uploaded";
             return ELLC_ERR_NOT_READY;
         }
-        if (q.flags & (ELLC_PAIR_CONST_WEIGHT | ELLC_PAIR_SAVE_WEIGHTS)) {
-            h->err = "constant-weight loop-closure variant is not built yet";
+        if ((q.flags & ELLC_PAIR_CONST_WEIGHT) && (q.flags & ELLC_PAIR_SAVE_WEIGHTS)) {
+            h->err = "a pair cannot both use constant weights and save weights (src/ImageFunc.cpp:241, :280)";
             return ELLC_ERR_INVALID;
+        }
+        if ((q.flags & ELLC_PAIR_CONST_WEIGHT) && !h->kf_lc_ready[q.kf_slot]) {
+            h->err = "constant-weight pair on a keyframe without loop-closure records: call ellc_prepare_keyframes_lc after the keyframe's last upload";
+            return ELLC_ERR_NOT_READY;
         }
     }
     return ELLC_OK;
@@ -399,14 +427,27 @@ static int track_launch(ellc_handle* h, int n, const ellc_pair* pairs, bool want
     // Schedule: frame-major, keyframe-minor.  Pairs are independent, so the order is free; putting the K pairs of one
     // frame on adjacent CTAs makes them share that frame's texel pyramid in L2 (and, with few keyframes, the keyframe
     // selection lists stay L2-resident as well).  Results are still written at the caller's pair index.
+    // Constant-weight (loop-closure) pairs run in their own kernel: the schedule lists the forward pairs first.
+    int n_fwd = 0;
+    bool save_weights = false;
     {
         std::vector<int> order(n);
         for (int i = 0; i < n; ++i) order[i] = i;
         std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+            const int la = (pairs[a].flags & ELLC_PAIR_CONST_WEIGHT) ? 1 : 0, lb = (pairs[b].flags & ELLC_PAIR_CONST_WEIGHT) ? 1 : 0;
+            if (la != lb) return la < lb;
             if (pairs[a].frame_slot != pairs[b].frame_slot) return pairs[a].frame_slot < pairs[b].frame_slot;
             return pairs[a].kf_slot < pairs[b].kf_slot;
         });
+        for (int i = 0; i < n; ++i) {
+            if (!(pairs[i].flags & ELLC_PAIR_CONST_WEIGHT)) ++n_fwd;
+            if (pairs[i].flags & ELLC_PAIR_SAVE_WEIGHTS) save_weights = true;
+        }
         rc = stage_h2d(h, h->d_order, order.data(), (size_t)n * sizeof(int));
+        if (rc) return rc;
+    }
+    if (save_weights || n_fwd < n) {
+        rc = ensure_lc_pools(h);
         if (rc) return rc;
     }
     if (want_trace) CU_TRY(h, cudaMemsetAsync(h->d_trace, 0, (size_t)n * kLevels * ELLC_MAX_TRACE_ITERS * sizeof(ellc_iter_trace), h->stream));
@@ -422,15 +463,23 @@ static int track_launch(ellc_handle* h, int n, const ellc_pair* pairs, bool want
     fill_params(h, p);
     p.pairs = h->d_pairs; p.order = h->d_order; p.results = h->d_results; p.trace = want_trace ? h->d_trace : nullptr; p.n_pairs = n;
     CU_TRY(h, cudaEventRecord(h->ev0, h->stream));
-    const int cluster = pick_cluster(h, n);
-    p.pairs_per_cta = pick_pairs_per_cta(h, n, cluster);
+    p.n_pairs = n_fwd;
+    const int cluster = pick_cluster(h, n_fwd);
+    p.pairs_per_cta = pick_pairs_per_cta(h, n_fwd, cluster);
     // diagnostics (tools/gpu_solve_cost.sh): fixed iteration counts with / without the solve
     if (const char* e = std::getenv("ELLC_DEBUG_NO_UPDATE")) if (*e == '1') p.no_update = 1;
     if (const char* e = std::getenv("ELLC_DEBUG_MAX_ITER")) std::sscanf(e, "%d,%d,%d,%d", &p.max_iter[0], &p.max_iter[1], &p.max_iter[2], &p.max_iter[3]);
     if (const char* e = std::getenv("ELLC_DEBUG_NO_STOP")) if (*e == '1') p.stop_threshold = -1.0f;
-    const int l = launch_track(h->stream, p, cluster, h->cfg.arithmetic == ELLC_ARITH_STRICT);
+    int l = launch_track(h->stream, p, cluster, h->cfg.arithmetic == ELLC_ARITH_STRICT);
     if (l < 0) { h->err = std::string("track kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()); return ELLC_ERR_CUDA; }
     h->launches += l;
+    if (n_fwd < n) {
+        p.order = h->d_order + n_fwd;
+        p.n_pairs = n - n_fwd;
+        l = launch_track_lc(h->stream, p, h->cfg.arithmetic == ELLC_ARITH_STRICT);
+        if (l < 0) { h->err = std::string("loop-closure track kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()); return ELLC_ERR_CUDA; }
+        h->launches += l;
+    }
     CU_TRY(h, cudaEventRecord(h->ev1, h->stream));
     CU_TRY(h, cudaEventRecord(h->batch_ev[seq & 3], h->stream));
     h->batch_seq = seq;
@@ -471,6 +520,7 @@ int ellc_upload_keyframe(ellc_handle* h, int32_t slot, const uint8_t* image, con
         CU_TRY(h, cudaMemcpyAsync(h->kf_var + slot * win + h->geo.win_off[l], var[l], bytes, cudaMemcpyHostToDevice, h->copy_stream));
     }
     h->kf_state[slot] = 1;
+    h->kf_lc_ready[slot] = 0;                              // the loop-closure records describe the previous contents
     h->kf_dirty.push_back(slot);
     return after_upload(h);
 }
@@ -686,6 +736,127 @@ void ellc_se3_exp(const float pose[6], float T[16]) {
 int64_t ellc_launch_count(const ellc_handle* h) { return h ? h->launches : 0; }
 void ellc_reset_launch_count(ellc_handle* h) { if (h) h->launches = 0; }
 void* ellc_stream(ellc_handle* h) { return h ? (void*)h->stream : nullptr; }
+// ---- keyframe weight pyramid and loop-closure records ---------------------------------------------------------------
+static int check_kf(ellc_handle* h, int32_t slot) {
+    if (slot < 0 || slot >= h->cfg.max_keyframes) { h->err = "bad keyframe slot"; return ELLC_ERR_INVALID; }
+    if (h->kf_state[slot] == 0) { h->err = "keyframe slot empty"; return ELLC_ERR_NOT_READY; }
+    return ELLC_OK;
+}
+
+int ellc_reset_keyframe_weights(ellc_handle* h, int32_t kf_slot) {
+    if (!h) return ELLC_ERR_INVALID;
+    if (kf_slot < 0 || kf_slot >= h->cfg.max_keyframes) { h->err = "bad keyframe slot"; return ELLC_ERR_INVALID; }
+    CU_TRY(h, cudaSetDevice(h->cfg.device));
+    int rc = ensure_lc_pools(h);
+    if (rc) return rc;
+    const int64_t win = h->geo.win_off[kLevels];
+    CU_TRY(h, cudaMemsetAsync(h->kf_weight + kf_slot * win, 0, (size_t)win * sizeof(float), h->stream));
+    for (int l = 0; l < kLevels; ++l) h->kf_wcount[(size_t)kf_slot * kLevels + l] = 0;
+    h->kf_lc_ready[kf_slot] = 0;
+    return ELLC_OK;
+}
+
+int ellc_accumulate_weights(ellc_handle* h, int32_t kf_slot, int32_t n, const int32_t* frame_slots) {
+    if (!h) return ELLC_ERR_INVALID;
+    int rc = check_kf(h, kf_slot);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && !frame_slots) || n > h->slots_cap) { h->err = "bad frame slot list"; return ELLC_ERR_INVALID; }
+    for (int i = 0; i < n; ++i)
+        if (frame_slots[i] < 0 || frame_slots[i] >= h->cfg.max_frames) { h->err = "frame slot out of range"; return ELLC_ERR_INVALID; }
+    if (n == 0) return ELLC_OK;
+    CU_TRY(h, cudaSetDevice(h->cfg.device));
+    rc = ensure_lc_pools(h);
+    if (rc) return rc;
+    rc = flush_dirty(h);                                   // the keyframe's mask must be current
+    if (rc) return rc;
+    rc = stage_h2d(h, h->d_slots, frame_slots, (size_t)n * sizeof(int));
+    if (rc) return rc;
+    const int64_t win = h->geo.win_off[kLevels];
+    h->launches += launch_accumulate_weights(h->stream, h->kf_weight + kf_slot * win, h->kf_mask + kf_slot * win, h->fr_weight, win, h->d_slots, n);
+    CU_TRY(h, cudaGetLastError());
+    for (int l = 0; l < kLevels; ++l) h->kf_wcount[(size_t)kf_slot * kLevels + l] += n;          // numWeightsAdded[level]++ per frame
+    h->kf_lc_ready[kf_slot] = 0;
+    return ELLC_OK;
+}
+
+int ellc_finalise_weights(ellc_handle* h, int32_t kf_slot) {
+    if (!h) return ELLC_ERR_INVALID;
+    int rc = check_kf(h, kf_slot);
+    if (rc) return rc;
+    CU_TRY(h, cudaSetDevice(h->cfg.device));
+    rc = ensure_lc_pools(h);
+    if (rc) return rc;
+    h->launches += launch_finalise_weights(h->stream, h->kf_weight + kf_slot * h->geo.win_off[kLevels], &h->kf_wcount[(size_t)kf_slot * kLevels], h->geo);
+    CU_TRY(h, cudaGetLastError());
+    h->kf_lc_ready[kf_slot] = 0;
+    return ELLC_OK;
+}
+
+int ellc_upload_keyframe_weights(ellc_handle* h, int32_t kf_slot, const float* const weight[ELLC_LEVELS], const int32_t counts[ELLC_LEVELS]) {
+    if (!h) return ELLC_ERR_INVALID;
+    if (kf_slot < 0 || kf_slot >= h->cfg.max_keyframes || !weight) { h->err = "bad keyframe slot / null weights"; return ELLC_ERR_INVALID; }
+    for (int l = 0; l < kLevels; ++l) if (!weight[l]) { h->err = "null weight level"; return ELLC_ERR_INVALID; }
+    CU_TRY(h, cudaSetDevice(h->cfg.device));
+    int rc = ensure_lc_pools(h);
+    if (rc) return rc;
+    const int64_t win = h->geo.win_off[kLevels];
+    for (int l = 0; l < kLevels; ++l) {
+        const size_t bytes = (size_t)(h->geo.win_off[l + 1] - h->geo.win_off[l]) * sizeof(float);
+        CU_TRY(h, cudaMemcpyAsync(h->kf_weight + kf_slot * win + h->geo.win_off[l], weight[l], bytes, cudaMemcpyHostToDevice, h->stream));
+        h->kf_wcount[(size_t)kf_slot * kLevels + l] = counts ? counts[l] : 0;
+    }
+    CU_TRY(h, cudaStreamSynchronize(h->stream));           // caller-owned pageable buffers may be released on return
+    h->kf_lc_ready[kf_slot] = 0;
+    return ELLC_OK;
+}
+
+int ellc_read_keyframe_weights(ellc_handle* h, int32_t kf_slot, int32_t level, float* weight, int32_t* count) {
+    if (!h) return ELLC_ERR_INVALID;
+    if (kf_slot < 0 || kf_slot >= h->cfg.max_keyframes || level < 0 || level >= kLevels) { h->err = "bad slot/level"; return ELLC_ERR_INVALID; }
+    CU_TRY(h, cudaSetDevice(h->cfg.device));
+    int rc = ensure_lc_pools(h);
+    if (rc) return rc;
+    const size_t npx = (size_t)(h->geo.win_off[level + 1] - h->geo.win_off[level]);
+    if (weight) CU_TRY(h, cudaMemcpyAsync(weight, h->kf_weight + kf_slot * h->geo.win_off[kLevels] + h->geo.win_off[level], npx * sizeof(float),
+                                          cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    if (count) *count = h->kf_wcount[(size_t)kf_slot * kLevels + level];
+    return ELLC_OK;
+}
+
+int ellc_read_frame_weights(ellc_handle* h, int32_t frame_slot, int32_t level, float* weight) {
+    if (!h) return ELLC_ERR_INVALID;
+    if (frame_slot < 0 || frame_slot >= h->cfg.max_frames || level < 0 || level >= kLevels || !weight) { h->err = "bad slot/level"; return ELLC_ERR_INVALID; }
+    CU_TRY(h, cudaSetDevice(h->cfg.device));
+    int rc = ensure_lc_pools(h);
+    if (rc) return rc;
+    const size_t npx = (size_t)(h->geo.win_off[level + 1] - h->geo.win_off[level]);
+    CU_TRY(h, cudaMemcpyAsync(weight, h->fr_weight + frame_slot * h->geo.win_off[kLevels] + h->geo.win_off[level], npx * sizeof(float),
+                              cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return ELLC_OK;
+}
+
+int ellc_prepare_keyframes_lc(ellc_handle* h, int32_t n, const int32_t* kf_slots) {
+    if (!h) return ELLC_ERR_INVALID;
+    if (n < 0 || (n > 0 && !kf_slots) || n > h->slots_cap) { h->err = "bad keyframe slot list"; return ELLC_ERR_INVALID; }
+    for (int i = 0; i < n; ++i) { int rc = check_kf(h, kf_slots[i]); if (rc) return rc; }
+    if (n == 0) return ELLC_OK;
+    CU_TRY(h, cudaSetDevice(h->cfg.device));
+    int rc = ensure_lc_pools(h);
+    if (rc) return rc;
+    rc = flush_dirty(h);                                   // selection lists of the current depth
+    if (rc) return rc;
+    int* d_slots = h->d_slots + h->slots_cap;
+    rc = stage_h2d(h, d_slots, kf_slots, (size_t)n * sizeof(int));
+    if (rc) return rc;
+    h->launches += launch_lc_prepare(h->stream, h->kf_geo, h->kf_pix, h->geo.win_off[kLevels], h->kf_count, h->kf_img, h->geo.img_off[kLevels],
+                                     h->kf_weight, h->kf_lc, h->kf_lcH, h->K, d_slots, n, h->geo);
+    CU_TRY(h, cudaGetLastError());
+    for (int i = 0; i < n; ++i) h->kf_lc_ready[kf_slots[i]] = 1;
+    return ELLC_OK;
+}
+
 int ellc_selftest_division(ellc_handle* h, int64_t n, uint64_t seed, int64_t mismatches[2]) {
     if (!h) return ELLC_ERR_INVALID;
     if (n < 0 || !mismatches) { h->err = "bad self-test arguments"; return ELLC_ERR_INVALID; }

@@ -46,7 +46,17 @@ constexpr int kTexTail = 4096;  // mapped words behind the last slot (weight-0 t
 __host__ __device__ inline int tex_I(uint32_t w) { return (int)(w >> 24); }
 __host__ __device__ inline int tex_gx2(uint32_t w) { return (int)(w & 0x3ffu) - 512; }
 __host__ __device__ inline int tex_gy2(uint32_t w) { return (int)((w >> 10) & 0x3ffu) - 512; }
-constexpr int kRecTail = 8192;  // mapped records behind the last keyframe slot (the pixel loop prefetches past a level's end)
+constexpr int kRecTail = 8192;
+
+// Loop-closure (inverse-compositional, constant-weight) record of one selected keyframe pixel, built once per keyframe by
+// lc_prepare_kernel: the steepest-descent row of src/PixelWisePyramid.cpp:633-666 (keyframe gradients at the keyframe
+// pixel: it does not depend on the pose) and the keyframe's finalised weight (weight_pyramid[level], :668).
+struct __align__(16) LcRec {
+    float J[6];
+    float w;
+    float pad;
+};
+static_assert(sizeof(LcRec) == 32, "LcRec must be 32 bytes");  // mapped records behind the last keyframe slot (the pixel loop prefetches past a level's end)
 
 // Geometry of the pyramid for one configuration.
 struct Geometry {
@@ -96,6 +106,9 @@ struct TrackParams {
     int iter_limit;            // 0 = use max_iter
     int no_update;
     float* weight_out;         // optional display_weightimg of the evaluated level (cols x rows), evaluate-only mode
+    float* frw_pool;           // per frame slot: display_weightimg of every level (win layout) for ELLC_PAIR_SAVE_WEIGHTS pairs
+    const LcRec* lc_pool;      // loop-closure records, per keyframe slot (rec_slot_stride)
+    const float* lc_H;         // [kf_slot][kLevels][36] precomputed hessian (src/PixelWisePyramid.cpp:938)
     uint32_t zero_mask;        // always 0: an opaque zero the pixel loop uses to build ordering dependences
 };
 

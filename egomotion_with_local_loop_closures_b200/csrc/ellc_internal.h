@@ -14,6 +14,13 @@ int launch_select(cudaStream_t st, const float* depth_pool, const float* var_poo
                   int* rowoff_pool, int* count_pool, SelGeo* geo_pool, SelPix* pix_pool, float* ikf_pool, const LevelK* K,
                   const int* d_slots, int n, const Geometry& geo);
 
+// keyframe weight pyramid (src/PixelWisePyramid.cpp:546-548, src/Frame.cpp:678-695) and loop-closure records (:561-680, :938)
+int launch_accumulate_weights(cudaStream_t st, float* kf_weight_slot, const uint8_t* mask_slot, const float* frw_pool,
+                              int64_t win, const int* d_frame_slots, int n);
+int launch_finalise_weights(cudaStream_t st, float* kf_weight_slot, const int counts[kLevels], const Geometry& geo);
+int launch_lc_prepare(cudaStream_t st, const SelGeo* geo_pool, const SelPix* pix_pool, int64_t rec_slot_stride, const int* count_pool,
+                      const uint8_t* img_pool, int64_t img_slot_stride, const float* weight_pool, LcRec* lc_pool, float* lc_H,
+                      const LevelK* K, const int* d_slots, int n, const Geometry& geo);
 // dst (device, 4-byte aligned, capacity rounded up to 4 bytes) <- pinned host memory read by the SMs (no copy engine)
 int launch_pull_host(cudaStream_t st, void* dst, const void* src_host_devptr, size_t bytes);
 
@@ -21,6 +28,8 @@ int launch_pull_host(cudaStream_t st, void* dst, const void* src_host_devptr, si
 // Launches the GN tracking kernel for p.n_pairs pairs with `cluster` CTAs per pair.  Returns kernels launched (1) or a
 // negative value on launch-configuration failure (cudaGetLastError carries the reason).
 int launch_track(cudaStream_t st, const TrackParams& p, int cluster, bool strict);
+// loop-closure (inverse-compositional constant-weight) variant: one CTA per pair, pairs = p.order[0 .. p.n_pairs)
+int launch_track_lc(cudaStream_t st, const TrackParams& p, bool strict);
 // single-thread kernel running solve_update_f on the device (ellc_solve_update)
 // div2_rn_shared (the pixel loop's shared-reciprocal exact division) against __fdiv_rn on n pseudo-random operand triples
 int launch_div_selftest(cudaStream_t st, long long n, unsigned long long seed, unsigned long long* d_counts /*[2]*/);

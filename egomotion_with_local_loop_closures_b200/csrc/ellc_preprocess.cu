@@ -333,6 +333,113 @@ select_write_kernel(const float* __restrict__ depth_pool, const float* __restric
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Keyframe weight pyramid and loop-closure records (the constant-weight variant, src/PixelWisePyramid.cpp:500-680, :938).
+// ------------------------------------------------------------------------------------------------------------------
+// saveWeights(true), :546-548: weight_pyramid[level] += display_weightimg, once per tracked frame, in the caller's frame
+// order (fp32, so the order is part of the result).  display_weightimg is zero where the mask is (:209-221); the frame
+// slot's weight image is only written at selected pixels, so the keyframe's mask supplies the zeros.
+__global__ void __launch_bounds__(256)
+accumulate_weights_kernel(float* __restrict__ kf_w, const uint8_t* __restrict__ mask, const float* __restrict__ frw_pool,
+                          int64_t win, const int* __restrict__ frame_slots, int n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= win) return;
+    float w = kf_w[i];
+    const bool sel = mask[i] != 0;
+    for (int f = 0; f < n; ++f) w = __fadd_rn(w, sel ? frw_pool[(int64_t)frame_slots[f] * win + i] : 0.0f);
+    kf_w[i] = w;
+}
+
+// frame::finaliseWeights, src/Frame.cpp:678-695: weight_pyramid[level] /= numWeightsAdded[level] when it is > 0
+struct Counts4 { int c[kLevels]; };
+__global__ void __launch_bounds__(256) finalise_weights_kernel(float* __restrict__ kf_w, Counts4 cnt, Geometry geo) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= geo.win_off[kLevels]) return;
+    int level = 0;
+#pragma unroll
+    for (int l = 1; l < kLevels; ++l) level += (i >= geo.win_off[l]);
+    if (cnt.c[level] > 0) kf_w[i] = __fdiv_rn(kf_w[i], (float)cnt.c[level]);
+}
+
+// precomputePixelWiseInvCompositional (:561-680) for the selected pixels of one keyframe level, in selection-list order, plus
+// hessian = weightedSteepestDescent * steepestDescent^T (:938).  cv::gemm on CV_32F accumulates the float x float products in
+// double and rounds once, so the sum is taken in double here too (the order of a double sum of ~1e5 float products does not
+// reach the fp32 result).  One CTA per (level, keyframe); the Jacobian follows the reference's operation sequence exactly
+// (fp32, with the sub-expressions C++ promotes to double through pow()).
+__global__ void __launch_bounds__(256)
+lc_prepare_kernel(const SelGeo* __restrict__ geo_pool, const SelPix* __restrict__ pix_pool, int64_t rec_slot_stride,
+                  const int* __restrict__ count_pool, const uint8_t* __restrict__ img_pool, int64_t img_slot_stride,
+                  const float* __restrict__ weight_pool, LcRec* __restrict__ lc_pool, float* __restrict__ lc_H, KSet ks,
+                  const int* __restrict__ slots, Geometry geo) {
+    const int level = blockIdx.x, slot = slots[blockIdx.y];
+    const LevelK K = ks.k[level];
+    const int cols = geo.cols[level], rows = geo.rows[level], stride = geo.pyr_w[level];
+    const int n = count_pool[slot * kLevels + level];
+    const int64_t rec_off = (int64_t)slot * rec_slot_stride + geo.win_off[level];
+    const uint8_t* __restrict__ img = img_pool + (int64_t)slot * img_slot_stride + geo.img_off[level];
+    const float* __restrict__ wimg = weight_pool + (int64_t)slot * geo.win_off[kLevels] + geo.win_off[level];
+    double Hd[36];
+#pragma unroll
+    for (int i = 0; i < 36; ++i) Hd[i] = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const SelPix px = pix_pool[rec_off + i];
+        const int x = selpix_x(px), y = selpix_y(px);
+        const float dep = geo_pool[rec_off + i].depth;
+        // prev_frame->gradientx/y at (x, y): frame::calculateGradient, src/Frame.cpp:185-285
+        const uint8_t* r = img + (int64_t)y * stride;
+        const int c = r[x];
+        int gx2, gy2;
+        if (x == 0) gx2 = 2 * ((int)r[1] - c);
+        else if (x == cols - 1) gx2 = 2 * (c - (int)r[x - 1]);
+        else gx2 = (int)r[x + 1] - (int)r[x - 1];
+        if (y == 0) gy2 = 2 * ((int)r[stride + x] - c);
+        else if (y == rows - 1) gy2 = 2 * (c - (int)r[x - stride]);
+        else gy2 = (int)r[stride + x] - (int)r[x - stride];
+        const float gradx = 0.5f * (float)gx2, grady = 0.5f * (float)gy2;
+        // :639-666
+        const float xc = __fsub_rn((float)x, K.cx), yc = __fsub_rn((float)y, K.cy);
+        const double dfx = K.fx, dfy = K.fy, dgx = gradx, dgy = grady, dxc = xc, dyc = yc;
+        const double idep = __ddiv_rn(1.0, (double)dep);
+        const float jb0 = (float)__dmul_rn(dgy, -__dadd_rn(dfy, __ddiv_rn(__dmul_rn(dyc, dyc), dfy)));
+        const float jt0 = __fmul_rn(gradx, __fdiv_rn(-__fmul_rn(yc, xc), K.fy));
+        const float jb1 = __fmul_rn(grady, __fdiv_rn(__fmul_rn(yc, xc), K.fx));
+        const float jt1 = (float)__dmul_rn(dgx, __dadd_rn(dfx, __ddiv_rn(__dmul_rn(dxc, dxc), dfx)));
+        const float jb2 = __fmul_rn(grady, __fdiv_rn(__fmul_rn(K.fy, xc), K.fx));
+        const float jt2 = __fmul_rn(gradx, -__fdiv_rn(__fmul_rn(K.fx, yc), K.fy));
+        const float jt3 = (float)__dmul_rn(dgx, __dmul_rn(dfx, idep));
+        const float jb4 = (float)__dmul_rn(dgy, __dmul_rn(dfy, idep));
+        const float jb5 = (float)__dmul_rn(dgy, __dmul_rn(-dyc, idep));
+        const float jt5 = (float)__dmul_rn(dgx, __dmul_rn(-dxc, idep));
+        LcRec rec;
+        rec.J[0] = __fadd_rn(jt0, jb0); rec.J[1] = __fadd_rn(jt1, jb1); rec.J[2] = __fadd_rn(jt2, jb2);
+        rec.J[3] = __fadd_rn(jt3, 0.f); rec.J[4] = __fadd_rn(0.f, jb4); rec.J[5] = __fadd_rn(jt5, jb5);
+        rec.w = wimg[y * cols + x];                                                    // weight_pyramid[level] :668
+        rec.pad = 0.f;
+        lc_pool[rec_off + i] = rec;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            const double wj = (double)__fmul_rn(rec.J[a], rec.w);                      // weightedSteepestDescent :668-673
+#pragma unroll
+            for (int b = 0; b < 6; ++b) Hd[a * 6 + b] = fma(wj, (double)rec.J[b], Hd[a * 6 + b]);
+        }
+    }
+    __shared__ double s_part[8][36];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 36; ++i) {
+        double v = Hd[i];
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) s_part[warp][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 36) {
+        double t = s_part[0][threadIdx.x];
+        for (int w = 1; w < 8; ++w) t += s_part[w][threadIdx.x];
+        lc_H[((int64_t)slot * kLevels + level) * 36 + threadIdx.x] = (float)t;
+    }
+}
+
 // Small host payloads (slot lists, pair lists, schedules) are pulled from the pinned staging arena by the SMs instead of
 // the copy engine: a cudaMemcpyAsync on the compute stream would queue in the one H2D engine behind the bulk image /
 // depth uploads of the NEXT batch (copy stream) and stall this batch's kernels for the whole upload burst.
@@ -400,6 +507,29 @@ int launch_select(cudaStream_t st, const float* depth_pool, const float* var_poo
                                                                 img_slot_stride, rowoff_pool, rows_total, geo_pool,
                                                                 pix_pool, ikf_pool, ks, d_slots, geo);
     return 3;
+}
+
+int launch_accumulate_weights(cudaStream_t st, float* kf_weight_slot, const uint8_t* mask_slot, const float* frw_pool,
+                              int64_t win, const int* d_frame_slots, int n) {
+    accumulate_weights_kernel<<<(unsigned)((win + 255) / 256), 256, 0, st>>>(kf_weight_slot, mask_slot, frw_pool, win, d_frame_slots, n);
+    return 1;
+}
+
+int launch_finalise_weights(cudaStream_t st, float* kf_weight_slot, const int counts[kLevels], const Geometry& geo) {
+    Counts4 c;
+    for (int l = 0; l < kLevels; ++l) c.c[l] = counts[l];
+    finalise_weights_kernel<<<(unsigned)((geo.win_off[kLevels] + 255) / 256), 256, 0, st>>>(kf_weight_slot, c, geo);
+    return 1;
+}
+
+int launch_lc_prepare(cudaStream_t st, const SelGeo* geo_pool, const SelPix* pix_pool, int64_t rec_slot_stride, const int* count_pool,
+                      const uint8_t* img_pool, int64_t img_slot_stride, const float* weight_pool, LcRec* lc_pool, float* lc_H,
+                      const LevelK* K, const int* d_slots, int n, const Geometry& geo) {
+    KSet ks;
+    for (int l = 0; l < kLevels; ++l) ks.k[l] = K[l];
+    lc_prepare_kernel<<<dim3(kLevels, n), 256, 0, st>>>(geo_pool, pix_pool, rec_slot_stride, count_pool, img_pool, img_slot_stride,
+                                                        weight_pool, lc_pool, lc_H, ks, d_slots, geo);
+    return 1;
 }
 
 }  // namespace ellc

@@ -158,6 +158,26 @@ int ellc_track_batch_async(ellc_handle* h, int32_t n, const ellc_pair* pairs, co
 int ellc_results_download(ellc_handle* h, const ellc_result* device_results, int32_t n, ellc_result* results);
 int ellc_synchronize(ellc_handle* h);
 
+/* ---- constant-weight loop-closure variant (src/PixelWisePyramid.cpp:500-974) --------------------------------------------------
+ * Reference flow with util::FLAG_DO_CONST_WEIGHT_POSE_ESTIMATION: every sequential track of a frame on its keyframe ends each
+ * level with saveWeights(true) (src/ImageFunc.cpp:280-288), which adds the level's last display_weightimg to the keyframe's
+ * weight_pyramid; when the keyframe is retired, frame::finaliseWeights (src/Frame.cpp:678-695, src/main.cpp:431-434) averages them;
+ * loop-closure pairs on that keyframe then run calculatePixelWiseParallelInvCompositional (src/ImageFunc.cpp:241-244).
+ * Here: flag the sequential pair ELLC_PAIR_SAVE_WEIGHTS (its weight images stay in the FRAME slot), call
+ * ellc_accumulate_weights with the frame slots in tracking order, ellc_finalise_weights, ellc_prepare_keyframes_lc, and flag the
+ * loop-closure pairs ELLC_PAIR_CONST_WEIGHT.  A keyframe upload invalidates the loop-closure records (not the weights). */
+int ellc_reset_keyframe_weights(ellc_handle* h, int32_t kf_slot);                /* Mat::zeros / numWeightsAdded = 0, src/Frame.cpp:114-122 */
+int ellc_accumulate_weights(ellc_handle* h, int32_t kf_slot, int32_t n, const int32_t* frame_slots);   /* saveWeights(true), :546-548;
+                                                                                     call before the keyframe's depth is replaced */
+int ellc_finalise_weights(ellc_handle* h, int32_t kf_slot);                      /* frame::finaliseWeights */
+/* Direct access to prev_frame->weight_pyramid[level] (cols x rows f32) / numWeightsAdded[level]. */
+int ellc_upload_keyframe_weights(ellc_handle* h, int32_t kf_slot, const float* const weight[ELLC_LEVELS], const int32_t counts[ELLC_LEVELS]);
+int ellc_read_keyframe_weights(ellc_handle* h, int32_t kf_slot, int32_t level, float* weight, int32_t* count);
+/* display_weightimg of the frame's last ELLC_PAIR_SAVE_WEIGHTS track; only pixels selected in its keyframe are written. */
+int ellc_read_frame_weights(ellc_handle* h, int32_t frame_slot, int32_t level, float* weight);
+/* precomputePixelWiseInvCompositional + hessian (:561-680, :938) for the keyframes' current depth and weights. */
+int ellc_prepare_keyframes_lc(ellc_handle* h, int32_t n, const int32_t* kf_slots);
+
 /* One evaluation of the normal equations at a given pose and level WITHOUT updating the pose: the body of
  * calculatePixelWiseParallel() up to src/PixelWisePyramid.cpp:442.  out->delta/pose_after/weighted_pose are left 0.
  * weight_image (host, (width>>level)*(height>>level) f32, display_weightimg :361) may be NULL. */

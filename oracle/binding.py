@@ -27,7 +27,8 @@ class Config(C.Structure):
                 ("max_iter", C.c_int * LEVELS),
                 ("huber_d", C.c_float), ("camera_pixel_noise_2", C.c_float),
                 ("weight", C.c_float * 6), ("stop_threshold", C.c_float),
-                ("num_bands", C.c_int), ("use_threads", C.c_int), ("jacobian_at_warped", C.c_int)]
+                ("num_bands", C.c_int), ("use_threads", C.c_int), ("jacobian_at_warped", C.c_int),
+                ("lc_parallel", C.c_int)]
 
 
 class Iter(C.Structure):
@@ -233,6 +234,50 @@ def track(cfg, kf_img0, cur_img0, depth_pyr, var_pyr, init_pose, want_trace=True
     lib().ellc_oracle_track(C.byref(cfg), _p(kf_img0), _p(cur_img0), dp, vp, _p(_f6(init_pose)), _p(out),
                             C.byref(tr) if want_trace else None)
     return out, (trace_to_dict(tr) if want_trace else None)
+
+
+def _pyr_ptrs(arrs, dtype):
+    keep = [np.ascontiguousarray(a, dtype) for a in arrs]
+    return keep, (C.c_void_p * LEVELS)(*[_p(a) for a in keep])
+
+
+def track_with_weights(cfg, kf_img0, cur_img0, depth_pyr, var_pyr, init_pose):
+    """Forward track + per level display_weightimg of the last executed iteration (what saveWeights(true) accumulates)."""
+    w, h = cfg.width, cfg.height
+    kfp, kfpp = _pyr_ptrs(image_pyramid(kf_img0), np.uint8)
+    cup, cupp = _pyr_ptrs(image_pyramid(cur_img0), np.uint8)
+    d, dp = _pyr_ptrs(depth_pyr, np.float32)
+    v, vp = _pyr_ptrs(var_pyr, np.float32)
+    wl = [np.zeros((h >> l, w >> l), np.float32) for l in range(LEVELS)]
+    wlp = (C.c_void_p * LEVELS)(*[_p(a) for a in wl])
+    out = np.empty(6, np.float32)
+    tr = Trace()
+    lib().ellc_oracle_track_weights_prebuilt(C.byref(cfg), kfpp, cupp, dp, vp, _p(_f6(init_pose)), _p(out), C.byref(tr), wlp)
+    return out, trace_to_dict(tr), wl
+
+
+def accumulate_weights(weight_pyr, counts, weight_last):
+    """saveWeights(true), src/PixelWisePyramid.cpp:546-548: weight_pyramid[l] += display_weightimg; numWeightsAdded[l]++."""
+    for l in range(LEVELS):
+        weight_pyr[l] = (weight_pyr[l].astype(np.float32) + weight_last[l].astype(np.float32)).astype(np.float32)
+        counts[l] += 1
+
+
+def finalise_weights(weight_pyr, counts):
+    """frame::finaliseWeights, src/Frame.cpp:678-695: weight_pyramid[l] /= numWeightsAdded[l] when > 0."""
+    return [(weight_pyr[l] / np.float32(counts[l])).astype(np.float32) if counts[l] > 0 else weight_pyr[l] for l in range(LEVELS)]
+
+
+def track_lc(cfg, kf_img0, cur_img0, depth_pyr, weight_pyr, init_pose):
+    """Inverse-compositional constant-weight tracker (loop-closure pairs)."""
+    kfp, kfpp = _pyr_ptrs(image_pyramid(kf_img0), np.uint8)
+    cup, cupp = _pyr_ptrs(image_pyramid(cur_img0), np.uint8)
+    d, dp = _pyr_ptrs(depth_pyr, np.float32)
+    wt, wp = _pyr_ptrs(weight_pyr, np.float32)
+    out = np.empty(6, np.float32)
+    tr = Trace()
+    lib().ellc_oracle_track_lc_prebuilt(C.byref(cfg), kfpp, cupp, dp, wp, _p(_f6(init_pose)), _p(out), C.byref(tr))
+    return out, trace_to_dict(tr)
 
 
 def track_many(cfg, kf_idx, fr_idx, kf_imgs, fr_imgs, kf_depth, kf_var, init_poses, n_workers=1):

@@ -381,7 +381,7 @@ void evaluate_level(const ellc_oracle_config* cfg, int level, const LevelView& l
 
 void track_impl(const ellc_oracle_config* cfg, const uint8_t* const* kf_pyr, const uint8_t* const* cur_pyr,
                 const float* const* depth, const float* const* var, const float init_pose[6],
-                float out_pose[6], ellc_oracle_trace* trace) {
+                float out_pose[6], ellc_oracle_trace* trace, float* const* weight_last = nullptr) {
     float pose[6];
     for (int i = 0; i < 6; ++i) pose[i] = init_pose[i];
     if (trace) std::memset(trace, 0, sizeof(*trace));
@@ -410,13 +410,161 @@ void track_impl(const ellc_oracle_config* cfg, const uint8_t* const* kf_pyr, con
         for (int iter = 0; iter < cfg->max_iter[level]; ++iter) {                 // ImageFunc.cpp:192
             ellc_oracle_iter local;
             ellc_oracle_iter* rec = (trace && iter < ELLC_ORACLE_MAX_ITERS) ? &trace->it[level][iter] : &local;
-            evaluate_level(cfg, level, lv, pose, rec, nullptr);
+            // display_weightimg is rewritten by every iteration; what saveWeights(true) adds at the end of the level
+            // (src/ImageFunc.cpp:280-288) is the image of the last executed one
+            evaluate_level(cfg, level, lv, pose, rec, weight_last ? weight_last[level] : nullptr);
             float Hinv[36];
             ellc_oracle_invert6(rec->H, Hinv);                                    // PixelWisePyramid.cpp:451
             ellc_oracle_update_pose(cfg, Hinv, rec->b, pose, rec->delta, &rec->weighted_pose);   // :453
             for (int i = 0; i < 6; ++i) rec->pose_after[i] = pose[i];
             ++executed;
             if (rec->weighted_pose < cfg->stop_threshold) break;                  // ImageFunc.cpp:251-252
+        }
+        if (trace) trace->n_iters[level] = executed;
+    }
+    for (int i = 0; i < 6; ++i) out_pose[i] = pose[i];
+    if (trace) for (int i = 0; i < 6; ++i) trace->final_pose[i] = pose[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// inverse-compositional constant-weight variant, src/PixelWisePyramid.cpp:561-974
+// ------------------------------------------------------------------------------------------------
+struct LcBand { float b[6]; double bd[6]; float res_f32; double res_f64; int n_oob; };
+
+// iteratePixelWiseInvCompositional, :687-913, rows [ymin, ymax)
+void lc_iterate_band(const Intr& K, const LevelView& lv, const float* weight, const float* J /* 6 x (rows*cols) */,
+                     const float SE3v[12], int ymin, int ymax, LcBand* acc) {
+    std::memset(acc, 0, sizeof(*acc));
+    const float fx = K.fx, fy = K.fy, cx = K.cx, cy = K.cy;
+    const size_t np = (size_t)lv.rows * lv.cols;
+    for (int y = ymin; y < ymax; ++y) {
+        for (int x = 0; x < lv.cols; ++x) {
+            const int idx = x + lv.cols * y;
+            if (lv.mask[idx] == 0) continue;                                          // :803-812
+            const float dep = lv.depth[idx];
+            float wX = (x - cx) * dep / fx;                                           // :824-826
+            float wY = (y - cy) * dep / fy;
+            float wZ = dep;
+            float tX = ((SE3v[0] * wX) + (SE3v[1] * wY) + (SE3v[2] * wZ) + (SE3v[3]));   // :833-855
+            float tY = ((SE3v[4] * wX) + (SE3v[5] * wY) + (SE3v[6] * wZ) + (SE3v[7]));
+            float tZ = ((SE3v[8] * wX) + (SE3v[9] * wY) + (SE3v[10] * wZ) + (SE3v[11]));
+            tZ = unzero(tZ);
+            float u = ((tX / tZ) * fx) + cx;
+            float v = ((tY / tZ) * fy) + cy;
+            float Iw = ellc_oracle_interp_u8(lv.cur, lv.cur_stride, lv.rows, lv.cols, u, v, 1);   // :862
+            const bool oob = (Iw == -1);
+            float residual = oob ? 0.0f : Iw - float(lv.kf[x + lv.kf_stride * y]);    // :873-878
+            if (oob) acc->n_oob++;
+            const float rw = residual * weight[idx];                                  // :890 residual*weight_ptr[x]
+            for (int i = 0; i < 6; ++i) {
+                const float t = J[i * np + idx] * rw;                                 // steepestdescentMat.mul(...)
+                acc->b[i] += t;
+                acc->bd[i] += (double)t;
+            }
+            const float term = weight[idx] * residual * residual;
+            acc->res_f32 += term;
+            acc->res_f64 += (double)term;
+        }
+    }
+}
+
+void track_lc_impl(const ellc_oracle_config* cfg, const uint8_t* const* kf_pyr, const uint8_t* const* cur_pyr,
+                   const float* const* depth, const float* const* weight, const float init_pose[6],
+                   float out_pose[6], ellc_oracle_trace* trace) {
+    float pose[6];
+    for (int i = 0; i < 6; ++i) pose[i] = init_pose[i];
+    if (trace) std::memset(trace, 0, sizeof(*trace));
+    int pw[ELLC_ORACLE_LEVELS];
+    pw[0] = cfg->width;
+    for (int l = 1; l < ELLC_ORACLE_LEVELS; ++l) pw[l] = (pw[l - 1] + 1) / 2;
+
+    std::vector<float> gx, gy, J;
+    std::vector<uint8_t> mask;
+    for (int level = ELLC_ORACLE_LEVELS - 1; level >= 0; --level) {
+        LevelView lv;
+        lv.rows = (int)(cfg->height / std::pow(2.0, level));
+        lv.cols = (int)(cfg->width / std::pow(2.0, level));
+        lv.kf = kf_pyr[level]; lv.kf_stride = pw[level];
+        lv.cur = cur_pyr[level]; lv.cur_stride = pw[level];
+        lv.depth = depth[level]; lv.var = nullptr;
+        const size_t np = (size_t)lv.rows * lv.cols;
+        int count = 0;
+        build_level_mask(depth[level], (int)np, mask, &count);
+        lv.mask = mask.data();
+        // prev_frame->gradientx/y at this level (updationOnPyrChange -> calculateGradient, src/Frame.cpp:316-327)
+        gx.assign(np, 0.f); gy.assign(np, 0.f);
+        ellc_oracle_gradient(lv.kf, lv.kf_stride, lv.rows, lv.cols, gx.data(), gy.data());
+        lv.gx = nullptr; lv.gy = nullptr;
+        if (trace) trace->n_selected[level] = count;
+        const Intr K = level_intrinsics(cfg, level);
+        const float fx = K.fx, fy = K.fy, cx = K.cx, cy = K.cy;
+
+        // ---- precomputePixelWiseInvCompositional :561-680 (its three row bands write disjoint pixels) --------
+        J.assign(6 * np, 0.f);
+        double Hd[36];
+        for (int i = 0; i < 36; ++i) Hd[i] = 0.0;
+        for (int y = 0; y < lv.rows; ++y) {
+            for (int x = 0; x < lv.cols; ++x) {
+                const int idx = x + lv.cols * y;
+                if (mask[idx] == 0) continue;                                         // :613-631 (zeros)
+                const float gradx = gx[idx], grady = gy[idx], dep = lv.depth[idx];
+                const float yc = -cy + y, xc = -cx + x;
+                const double idep = std::pow((double)dep, -1);
+                float jb[6], jt[6];
+                jb[0] = (float)(grady * (-(fy + (std::pow((double)yc, 2) / fy))));     // :639-657
+                jt[0] = gradx * (-(yc * xc) / fy);
+                jb[1] = grady * ((yc * xc) / fx);
+                jt[1] = (float)(gradx * (fx + (std::pow((double)xc, 2) / fx)));
+                jb[2] = grady * ((fy * xc) / fx);
+                jt[2] = gradx * (-(fx * yc / fy));
+                jb[3] = 0;
+                jt[3] = (float)(gradx * (fx * idep));
+                jb[4] = (float)(grady * (fy * idep));
+                jt[4] = 0;
+                jb[5] = (float)(grady * (-yc * idep));
+                jt[5] = (float)(gradx * (-xc * idep));
+                float Jp[6], wJ[6];
+                for (int i = 0; i < 6; ++i) { Jp[i] = jt[i] + jb[i]; J[i * np + idx] = Jp[i]; }     // :661-666
+                for (int i = 0; i < 6; ++i) wJ[i] = Jp[i] * weight[level][idx];                       // :668-673
+                // hessian = weightedSteepestDescent * steepestDescent.t() (:938): cv::gemm on CV_32F accumulates the
+                // float x float products in double (GEMMSingleMul<float,double> / GEMMBlockMul) and rounds once
+                for (int i = 0; i < 6; ++i)
+                    for (int j = 0; j < 6; ++j) Hd[i * 6 + j] += (double)wJ[i] * (double)Jp[j];
+            }
+        }
+        float H[36], Hinv[36];
+        for (int i = 0; i < 36; ++i) H[i] = (float)Hd[i];
+        ellc_oracle_invert6(H, Hinv);                                                 // :939
+
+        int executed = 0;
+        for (int iter = 0; iter < cfg->max_iter[level]; ++iter) {
+            ellc_oracle_iter local;
+            ellc_oracle_iter* rec = (trace && iter < ELLC_ORACLE_MAX_ITERS) ? &trace->it[level][iter] : &local;
+            std::memset(rec, 0, sizeof(*rec));
+            M4 T = mat_exp_f32(se3_hat(pose));                                        // :768-790
+            float SE3v[12];
+            for (int i = 0; i < 12; ++i) SE3v[i] = T.a[i];
+            LcBand band[2];
+            int nb = 1;
+            if (cfg->lc_parallel) {
+                const int inc = lv.rows / 3;                                          // :925 NUM_CONST_WT_POSE_EST_THREADS = 3
+                lc_iterate_band(K, lv, weight[level], J.data(), SE3v, 0, inc, &band[0]);          // :945
+                lc_iterate_band(K, lv, weight[level], J.data(), SE3v, inc, lv.rows, &band[1]);    // :946
+                nb = 2;
+            } else {
+                lc_iterate_band(K, lv, weight[level], J.data(), SE3v, 0, lv.rows, &band[0]);      // :970
+            }
+            for (int i = 0; i < 6; ++i) { rec->b[i] = band[0].b[i]; rec->b_f64[i] = band[0].bd[i]; }
+            rec->res_sum_f32 = band[0].res_f32; rec->res_sum_f64 = band[0].res_f64; rec->n_oob = band[0].n_oob;
+            if (nb == 2) {
+                for (int i = 0; i < 6; ++i) { rec->b[i] = rec->b[i] + band[1].b[i]; rec->b_f64[i] += band[1].bd[i]; }   // :951
+                rec->res_sum_f32 += band[1].res_f32; rec->res_sum_f64 += band[1].res_f64; rec->n_oob += band[1].n_oob;
+            }
+            for (int i = 0; i < 36; ++i) { rec->H[i] = H[i]; rec->H_f64[i] = Hd[i]; }
+            ellc_oracle_update_pose(cfg, Hinv, rec->b, pose, rec->delta, &rec->weighted_pose);       // :954
+            for (int i = 0; i < 6; ++i) rec->pose_after[i] = pose[i];
+            ++executed;
+            if (rec->weighted_pose < cfg->stop_threshold) break;                      // src/ImageFunc.cpp:251-252
         }
         if (trace) trace->n_iters[level] = executed;
     }
@@ -455,7 +603,7 @@ void ellc_oracle_default_config(ellc_oracle_config* c, int width, int height) {
     c->weight[0] = c->weight[1] = c->weight[2] = 100000.0f;                            // :76
     c->weight[3] = c->weight[4] = c->weight[5] = 10000.0f;
     c->stop_threshold = 1.0f;
-    c->num_bands = 3; c->use_threads = 0; c->jacobian_at_warped = 0;
+    c->num_bands = 3; c->use_threads = 0; c->jacobian_at_warped = 0; c->lc_parallel = 1;
 }
 
 void ellc_oracle_pyrdown_u8(const uint8_t* src, int w, int h, int src_stride, uint8_t* dst) {
@@ -681,6 +829,18 @@ void ellc_oracle_track_prebuilt(const ellc_oracle_config* cfg, const uint8_t* co
                                 const float* const* depth, const float* const* var,
                                 const float init_pose[6], float out_pose[6], ellc_oracle_trace* trace) {
     track_impl(cfg, kf_pyr, cur_pyr, depth, var, init_pose, out_pose, trace);
+}
+
+void ellc_oracle_track_weights_prebuilt(const ellc_oracle_config* cfg, const uint8_t* const* kf_pyr, const uint8_t* const* cur_pyr,
+                                        const float* const* depth, const float* const* var, const float init_pose[6],
+                                        float out_pose[6], ellc_oracle_trace* trace, float* const* weight_last) {
+    track_impl(cfg, kf_pyr, cur_pyr, depth, var, init_pose, out_pose, trace, weight_last);
+}
+
+void ellc_oracle_track_lc_prebuilt(const ellc_oracle_config* cfg, const uint8_t* const* kf_pyr, const uint8_t* const* cur_pyr,
+                                   const float* const* depth, const float* const* weight, const float init_pose[6],
+                                   float out_pose[6], ellc_oracle_trace* trace) {
+    track_lc_impl(cfg, kf_pyr, cur_pyr, depth, weight, init_pose, out_pose, trace);
 }
 
 void ellc_oracle_track(const ellc_oracle_config* cfg, const uint8_t* kf_img0, const uint8_t* cur_img0,
