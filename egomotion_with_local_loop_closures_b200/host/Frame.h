@@ -49,9 +49,11 @@ public:
     void calculatePoseWrtWorld(frame* prev_image, float* poseChangeWrtPrevframe, bool frmhomo = false);    // :352-372
     void concatenateRelativePose(float* src_1wrt2, float* src_2wrt3, float* dest_1wrt3);                   // :503-530
     void concatenateOriginPose(float* src_1wrt0, float* src_2wrt0, float* dest_1wrt2);                     // :534-562
+    void finaliseWeights();                               // src/Frame.cpp:678-695 (+ loop-closure records on the GPU)
 
     // residency in the B200 library (not part of the reference surface)
     int gpu_frame_slot, gpu_kf_slot;
     unsigned long long gpu_kf_stamp;                      // bumped by depthMap::markDepthUpdated()
+    bool gpu_lc_ready;                                    // weights finalised and loop-closure records built
     static int numberOfInstances;
 };

@@ -92,8 +92,10 @@ int keyframe_slot(frame* f, depthMap* dm) {
     if (s < 0 || g.kf_owner[s] != f) {
         s = g.next_kf;
         g.next_kf = (g.next_kf + 1) % kKfSlots;
-        if (g.kf_owner[s]) g.kf_owner[s]->gpu_kf_slot = -1;
+        if (g.kf_owner[s]) { g.kf_owner[s]->gpu_kf_slot = -1; g.kf_owner[s]->gpu_lc_ready = false; }
         g.kf_owner[s] = f; f->gpu_kf_slot = s;
+        f->gpu_lc_ready = false;                                             // a fresh slot holds no weights
+        if (ellc_reset_keyframe_weights(h, s) != ELLC_OK) fail("ellc_reset_keyframe_weights");
     }
     const float* dptr[4]; const float* vptr[4];
     std::vector<float> novar[4];
@@ -105,6 +107,10 @@ int keyframe_slot(frame* f, depthMap* dm) {
     if (ellc_upload_keyframe(h, s, f->image.ptr<uchar>(0), dptr, vptr) != ELLC_OK) fail("ellc_upload_keyframe");
     if (ellc_synchronize(h) != ELLC_OK) fail("ellc_synchronize");             // novar[] dies at scope exit
     g.kf_stamp[s] = stamp;
+    if (f->gpu_lc_ready) {                                                   // new depth: the loop-closure records follow it
+        const int32_t ks = s;
+        if (ellc_prepare_keyframes_lc(h, 1, &ks) != ELLC_OK) fail("ellc_prepare_keyframes_lc");
+    }
     return s;
 }
 
@@ -126,7 +132,7 @@ const char* last_error() { return g.err.c_str(); }
 int frame::numberOfInstances = 0;
 
 frame::frame() : frameId(0), parentKeyframeId(0), isKeyframe(false), width(0), height(0), currentRows(0), currentCols(0),
-                 pyrLevel(0), no_nonZeroDepthPts(0), rescaleFactor(1.0f), gpu_frame_slot(-1), gpu_kf_slot(-1), gpu_kf_stamp(0) {
+                 pyrLevel(0), no_nonZeroDepthPts(0), rescaleFactor(1.0f), gpu_frame_slot(-1), gpu_kf_slot(-1), gpu_kf_stamp(0), gpu_lc_ready(false) {
     for (int i = 0; i < 6; ++i) poseWrtOrigin[i] = poseWrtWorld[i] = 0.0f;
     for (int l = 0; l < util::MAX_PYRAMID_LEVEL; ++l) numWeightsAdded[l] = 0;
 }
@@ -144,6 +150,20 @@ frame::frame(const unsigned char* gray, int w, int h) : frame() {
         depth_pyramid[l] = Mat::zeros(h >> l, w >> l, ellc_host::CV_32FC1);
         weight_pyramid[l] = Mat::zeros(h >> l, w >> l, ellc_host::CV_32FC1);
     }
+}
+
+// frame::finaliseWeights, src/Frame.cpp:678-695 (called when the keyframe is retired, src/main.cpp:431-434): average the saved
+// weights, then build the keyframe's loop-closure records so that later loop-closure pairs on it run the constant-weight tracker.
+// weight_pyramid[] is read back so that callers looking at the member see what the reference would hold.
+void frame::finaliseWeights() {
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (gpu_kf_slot < 0) { std::printf("\nWeights cannot be averaged!!! "); return; }
+    const int32_t ks = gpu_kf_slot;
+    if (ellc_finalise_weights(ctx(), ks) != ELLC_OK) fail("ellc_finalise_weights");
+    if (ellc_prepare_keyframes_lc(ctx(), 1, &ks) != ELLC_OK) fail("ellc_prepare_keyframes_lc");
+    for (int l = 0; l < util::MAX_PYRAMID_LEVEL; ++l)
+        if (ellc_read_keyframe_weights(ctx(), ks, l, weight_pyramid[l].ptr<float>(0), nullptr) != ELLC_OK) fail("ellc_read_keyframe_weights");
+    gpu_lc_ready = true;
 }
 
 frame::~frame() {
@@ -275,11 +295,20 @@ std::vector<float> GetImagePoseEstimate(frame* prev_frame, frame* current_frame,
         ellc_pair pr;
         pr.kf_slot = keyframe_slot(prev_frame, currDepthMap);
         pr.frame_slot = frame_slot(current_frame);
-        pr.flags = ELLC_PAIR_DEFAULT;
+        // src/ImageFunc.cpp:241-244: loop-closure pairs use the constant-weight inverse-compositional tracker once the
+        // keyframe's weights are final; :280-288: sequential tracks save their last weights into the keyframe's pyramid
+        const bool cw = util::FLAG_DO_CONST_WEIGHT_POSE_ESTIMATION;
+        pr.flags = (cw && fromLoopClosure && prev_frame->gpu_lc_ready) ? ELLC_PAIR_CONST_WEIGHT
+                 : (cw && !fromLoopClosure) ? ELLC_PAIR_SAVE_WEIGHTS : ELLC_PAIR_DEFAULT;
         for (int i = 0; i < 6; ++i) pr.init_pose[i] = pose[i];
         ellc_result res;
         if (ellc_track_batch(ctx(), 1, &pr, &res, nullptr) != ELLC_OK) fail("ellc_track_batch");
         for (int i = 0; i < 6; ++i) pose[i] = res.pose[i];
+        if (pr.flags == ELLC_PAIR_SAVE_WEIGHTS) {                              // saveWeights(true), src/PixelWisePyramid.cpp:546-548
+            const int32_t fs = pr.frame_slot;
+            if (ellc_accumulate_weights(ctx(), pr.kf_slot, 1, &fs) != ELLC_OK) fail("ellc_accumulate_weights");
+            for (int l = 0; l < util::MAX_PYRAMID_LEVEL; ++l) prev_frame->numWeightsAdded[l]++;
+        }
     }
     // post-conditions the depth module relies on (src/ImageFunc.cpp:158-159 end at level 0)
     prev_frame->updationOnPyrChange(0);
@@ -298,7 +327,7 @@ std::vector<float> ellc_host::TrackPairsBatched(const std::vector<frame*>& keyfr
     for (size_t i = 0; i < n; ++i) {
         pairs[i].kf_slot = keyframe_slot(keyframes[i], depthMaps[i]);
         pairs[i].frame_slot = frame_slot(frames[i]);
-        pairs[i].flags = ELLC_PAIR_DEFAULT;
+        pairs[i].flags = (util::FLAG_DO_CONST_WEIGHT_POSE_ESTIMATION && keyframes[i]->gpu_lc_ready) ? ELLC_PAIR_CONST_WEIGHT : ELLC_PAIR_DEFAULT;
         for (int k = 0; k < 6; ++k) pairs[i].init_pose[k] = init_poses[i * 6 + k];
     }
     if (n && ellc_track_batch(ctx(), (int)n, pairs.data(), res.data(), nullptr) != ELLC_OK) fail("ellc_track_batch");

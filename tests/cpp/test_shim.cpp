@@ -58,6 +58,27 @@ int main(int argc, char** argv) {
                    pw.weightedPose, pw.residualSum, pw.hessian.ptr<float>(0)[0]);
         }
         printf("count2 %d\n", kf.no_nonZeroDepthPts);
+        // constant-weight loop-closure flow (FLAG_DO_CONST_WEIGHT_POSE_ESTIMATION): sequential tracks save their weights
+        // (src/ImageFunc.cpp:280-288), the keyframe is finalised (src/main.cpp:431-434), then a loop-closure pair runs the
+        // inverse-compositional tracker (src/ImageFunc.cpp:241-244)
+        util::FLAG_DO_CONST_WEIGHT_POSE_ESTIMATION = true;
+        prev = &kf;
+        for (int i = 0; i < n; ++i) {
+            float init[6] = {0, 0, 0, 0, 0, 0};
+            GetImagePoseEstimate(&kf, frames[i], i + 2, &dm, prev, init);
+            prev = frames[i];
+        }
+        kf.finaliseWeights();
+        printf("nweights %d %d\n", kf.numWeightsAdded[0], kf.numWeightsAdded[3]);
+        {
+            double ws = 0;
+            const float* wp0 = kf.weight_pyramid[1].ptr<float>(0);
+            for (int i = 0; i < (w >> 1) * (h >> 1); ++i) ws += wp0[i];
+            printf("wsum1 %.9g\n", ws);
+            float init[6] = {0, 0, 0, 0, 0, 0};
+            std::vector<float> p = GetImagePoseEstimate(&kf, frames[n - 1], 99, &dm, frames[0], init, true);
+            printf("lcpose %.9g %.9g %.9g %.9g %.9g %.9g\n", p[0], p[1], p[2], p[3], p[4], p[5]);
+        }
         for (frame* c : frames) delete c;
     } catch (const std::exception& e) {
         fprintf(stderr, "shim error: %s\n", e.what());

@@ -83,3 +83,22 @@ def test_shim_tracks_like_the_reference_driver(tmp_path, oracle_mod):
         assert abs(float(g[11]) - o["res_sum_f64"]) <= 1e-5 * o["res_sum_f64"]
         assert abs(float(g[13]) - o["H_f64"][0, 0]) <= 1e-5 * o["H_f64"][0, 0]
     assert [l for l in lines if l[0] == "count2"][0][1] == str(int((kf["depth"][2] > 0).sum()))
+    # constant-weight loop-closure flow: weights saved by the sequential tracks, finalised, then one loop-closure pair
+    h_, w_ = h, w
+    wp = [np.zeros((h_ >> l, w_ >> l), np.float32) for l in range(4)]
+    cnt = [0] * 4
+    prev_world = kf_world.copy()
+    worlds = []
+    for i in range(n):
+        init = oracle_mod.concat_origin(prev_world, kf_world)
+        opose, _, wl = oracle_mod.track_with_weights(ocfg, kf["image"], frames[i], kf["depth"], kf["var"], init)
+        oracle_mod.accumulate_weights(wp, cnt, wl)
+        prev_world = oracle_mod.concat_relative(opose, kf_world)
+        worlds.append(prev_world)
+    wf = oracle_mod.finalise_weights(wp, cnt)
+    assert [l for l in lines if l[0] == "nweights"][0][1:] == [str(n), str(n)]
+    assert abs(float([l for l in lines if l[0] == "wsum1"][0][1]) - float(wf[1].sum(dtype=np.float64))) <= 1e-4 * float(wf[1].sum(dtype=np.float64))
+    init = oracle_mod.concat_origin(worlds[0], kf_world)                      # t-1 frame of the loop-closure call = frame 0
+    opose, otr = oracle_mod.track_lc(ocfg, kf["image"], frames[n - 1], kf["depth"], wf, init)
+    got = np.array([l for l in lines if l[0] == "lcpose"][0][1:7], np.float64)
+    assert np.abs(got - opose).max() < 1e-4
