@@ -203,6 +203,9 @@ def main():
     ap.add_argument("--pairs-per-frame", type=int, default=9, help="1 sequential + K=8 loop-closure candidates")
     ap.add_argument("--arith", default="fast", choices=["fast", "strict"])
     ap.add_argument("--cluster", type=int, default=0)
+    ap.add_argument("--lc-mode", default="forward", choices=["forward", "const_weight"],
+                    help="const_weight: the K-1 loop-closure pairs of every frame run the reference's constant-weight "
+                         "inverse-compositional tracker (FLAG_DO_CONST_WEIGHT_POSE_ESTIMATION); not the headline workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -274,13 +277,32 @@ def main():
         for i in range(args.frames):
             trk.upload_frame(fo + i, h_frames[i])
 
-    pairs = trk.make_pairs(wl["kf_idx"], wl["fr_idx"], wl["init"])
+    lc = args.lc_mode == "const_weight"
+    primary = (wl["kf_idx"] == (wl["fr_idx"] % args.keyframes))
+    flags = np.where(primary, capi.PAIR_SAVE_WEIGHTS, capi.PAIR_CONST_WEIGHT).astype(np.int32) if lc else 0
+    pairs = trk.make_pairs(wl["kf_idx"], wl["fr_idx"], wl["init"], flags=flags)
     pairs_half = [pairs, trk.make_pairs(wl["kf_idx"] + args.keyframes, wl["fr_idx"] + args.frames, wl["init"])]
+    if lc:
+        args.no_e2e = True                                     # an upload invalidates the loop-closure records: resident mode only
+        args.no_cpu_baseline = True                            # (the forward CPU baseline is not this workload)
     fr_slots = np.arange(args.frames, dtype=np.int32)
     kf_slots = np.arange(args.keyframes, dtype=np.int32)
 
     upload_all()
     trk.synchronize()
+    if lc:
+        # untimed setup, as in the reference's flow: every keyframe's weight pyramid = average of the last-iteration weights of
+        # the sequential tracks of its frames (saveWeights / finaliseWeights), then the loop-closure records
+        seq = trk.make_pairs(wl["kf_idx"][primary], wl["fr_idx"][primary], wl["init"][primary], flags=capi.PAIR_SAVE_WEIGHTS)
+        trk.track_batch(seq)
+        for kslot in range(args.keyframes):
+            trk.reset_keyframe_weights(kslot)
+            fr = np.sort(wl["fr_idx"][primary][wl["kf_idx"][primary] == kslot])
+            for lo in range(0, len(fr), 64):
+                trk.accumulate_weights(kslot, fr[lo:lo + 64])
+            trk.finalise_weights(kslot)
+        trk.prepare_keyframes_lc(np.arange(args.keyframes, dtype=np.int32))
+        trk.synchronize()
     setup_s = time.time() - t_setup
 
     kernel_ms = []
@@ -288,6 +310,8 @@ def main():
     def step_resident():
         trk.prepare_frames(fr_slots)
         trk.prepare_keyframes(kf_slots)
+        if lc:
+            trk.prepare_keyframes_lc(kf_slots)                 # the per-keyframe Jacobians / hessians are part of the step
         if world > 1:
             dptr = trk.track_batch_async(pairs)
             trk.synchronize()
@@ -420,7 +444,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "pair_sweep_640x480", "width": W, "height": H, "keyframes_per_gpu": args.keyframes,
+                "config": {"workload": "pair_sweep_640x480" + ("_lc_const_weight" if lc else ""), "width": W, "height": H, "keyframes_per_gpu": args.keyframes,
                            "frames_per_gpu": args.frames, "pairs_per_gpu_per_step": n_pairs, "pairs_per_frame": args.pairs_per_frame,
                            "arithmetic": args.arith, "parallelism": f"pair list sharded by connected components (sequence segments) x{world}, NCCL all-gather of 256 B result records",
                            "l2": "inputs (%.0f MB per step per GPU) exceed the 126 MB L2; no flush" % (h2d_bytes / 1e6),
