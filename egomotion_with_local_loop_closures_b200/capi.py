@@ -67,7 +67,7 @@ SYMBOLS = ["ellc_default_config", "ellc_create", "ellc_destroy", "ellc_last_erro
            "ellc_read_keyframe_level", "ellc_level_dims", "ellc_concat_relative", "ellc_concat_origin",
            "ellc_se3_exp", "ellc_launch_count", "ellc_reset_launch_count", "ellc_stream", "ellc_stream_of", "ellc_selftest_division", "ellc_reset_keyframe_weights", "ellc_accumulate_weights",
            "ellc_finalise_weights", "ellc_upload_keyframe_weights", "ellc_read_keyframe_weights", "ellc_read_frame_weights",
-           "ellc_prepare_keyframes_lc", "ellc_last_track_kernel_ms"]
+           "ellc_prepare_keyframes_lc", "ellc_upload_keyframe_hypotheses", "ellc_read_keyframe_occupancy", "ellc_read_keyframe_depth", "ellc_last_track_kernel_ms"]
 
 _lib = None
 
@@ -116,6 +116,9 @@ def lib():
         L.ellc_read_keyframe_weights.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_int32)]
         L.ellc_read_frame_weights.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
         L.ellc_prepare_keyframes_lc.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        L.ellc_upload_keyframe_hypotheses.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 5
+        L.ellc_read_keyframe_occupancy.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_float)]
+        L.ellc_read_keyframe_depth.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
         L.ellc_selftest_division.argtypes = [C.c_void_p, C.c_int64, C.c_uint64, C.POINTER(C.c_int64)]
         L.ellc_stream_of.restype = C.c_void_p
         L.ellc_stream_of.argtypes = [C.c_void_p, C.c_int32]
@@ -306,6 +309,29 @@ class Tracker:
 
     def stream(self):
         return lib().ellc_stream(self._h)
+
+    # -- keyframe from depth hypotheses (depth / variance pyramids built on the device)
+    def upload_keyframe_hypotheses(self, slot, image, valid, inv_depth_smoothed, variance_smoothed, want_valid_out=False):
+        image = np.ascontiguousarray(image, np.uint8)
+        valid = np.ascontiguousarray(valid, np.uint8)
+        idep = np.ascontiguousarray(inv_depth_smoothed, np.float32)
+        vs = np.ascontiguousarray(variance_smoothed, np.float32)
+        assert image.shape == valid.shape == idep.shape == vs.shape == (self.cfg.height, self.cfg.width)
+        vout = np.zeros_like(valid) if want_valid_out else None
+        self._keep = getattr(self, "_keep", []) + [image, valid, idep, vs]
+        self._chk(lib().ellc_upload_keyframe_hypotheses(self._h, slot, _p(image), _p(valid), _p(idep), _p(vs), _p(vout) if want_valid_out else None))
+        return vout
+
+    def read_keyframe_occupancy(self, slot):
+        n, occ = C.c_int32(), C.c_float()
+        self._chk(lib().ellc_read_keyframe_occupancy(self._h, slot, C.byref(n), C.byref(occ)))
+        return n.value, occ.value
+
+    def read_keyframe_depth(self, slot, level):
+        shape = (self.cfg.height >> level, self.cfg.width >> level)
+        d, v = np.zeros(shape, np.float32), np.zeros(shape, np.float32)
+        self._chk(lib().ellc_read_keyframe_depth(self._h, slot, level, _p(d), _p(v)))
+        return d, v
 
     # -- constant-weight loop-closure variant
     def reset_keyframe_weights(self, kf_slot):

@@ -42,6 +42,9 @@ struct ellc_handle {
     // pools
     uint8_t* fr_img; uint32_t* fr_tex;
     uint8_t* kf_img; float* kf_depth; float* kf_var; uint8_t* kf_mask; SelGeo* kf_geo; SelPix* kf_pix; float* kf_ikf;
+    // hypothesis staging of ellc_upload_keyframe_hypotheses (allocated on first use) and per-slot valid counts
+    uint8_t* d_hyp; int* d_nvalid;
+    std::vector<int> kf_nvalid;                        // -1: not uploaded from hypotheses / not fetched yet
     // loop-closure state, allocated on first use (ensure_lc_pools)
     float* fr_weight; float* kf_weight; LcRec* kf_lc; float* kf_lcH;
     std::vector<int> kf_wcount;                        // numWeightsAdded[level] per keyframe slot
@@ -129,6 +132,7 @@ int ellc_destroy(ellc_handle* h) {
     if (h->d2h_stream) cudaStreamSynchronize(h->d2h_stream);
     cudaFree(h->fr_img); cudaFree(h->fr_tex); cudaFree(h->kf_img); cudaFree(h->kf_depth); cudaFree(h->kf_var);
     cudaFree(h->kf_mask); cudaFree(h->kf_geo); cudaFree(h->kf_pix); cudaFree(h->kf_ikf);
+    cudaFree(h->d_hyp); cudaFree(h->d_nvalid);
     cudaFree(h->fr_weight); cudaFree(h->kf_weight); cudaFree(h->kf_lc); cudaFree(h->kf_lcH); cudaFree(h->kf_count); cudaFree(h->kf_rowcount); cudaFree(h->kf_rowoff);
     cudaFree(h->d_slots); cudaFree(h->d_pairs); cudaFree(h->d_results2[0]); cudaFree(h->d_results2[1]); cudaFree(h->d_order); cudaFree(h->d_trace); cudaFree(h->d_small);
     cudaFree(h->d_weight);
@@ -194,6 +198,7 @@ int ellc_create(const ellc_config* cfg, ellc_handle** out) {
     h->fr_reader.assign(cfg->max_frames, 0);
     h->kf_wcount.assign((size_t)cfg->max_keyframes * kLevels, 0);
     h->kf_lc_ready.assign(cfg->max_keyframes, 0);
+    h->kf_nvalid.assign(cfg->max_keyframes, -1);
     h->kf_reader.assign(cfg->max_keyframes, 0);
     const int64_t img = h->geo.img_off[kLevels], win = h->geo.win_off[kLevels];
     const int64_t nf = cfg->max_frames, nk = cfg->max_keyframes;
@@ -521,8 +526,82 @@ int ellc_upload_keyframe(ellc_handle* h, int32_t slot, const uint8_t* image, con
     }
     h->kf_state[slot] = 1;
     h->kf_lc_ready[slot] = 0;                              // the loop-closure records describe the previous contents
+    h->kf_nvalid[slot] = -1;
     h->kf_dirty.push_back(slot);
     return after_upload(h);
+}
+
+int ellc_upload_keyframe_hypotheses(ellc_handle* h, int32_t slot, const uint8_t* image, const uint8_t* valid,
+                                    const float* inv_depth_smoothed, const float* variance_smoothed, uint8_t* valid_out) {
+    if (!h) return ELLC_ERR_INVALID;
+    if (!image || !valid || !inv_depth_smoothed || !variance_smoothed || slot < 0 || slot >= h->cfg.max_keyframes) {
+        h->err = "bad keyframe slot / null pointer"; return ELLC_ERR_INVALID;
+    }
+    CU_TRY(h, cudaSetDevice(h->cfg.device));
+    const int64_t npx = (int64_t)h->geo.width * h->geo.height, win = h->geo.win_off[kLevels];
+    if (!h->d_hyp) {
+        CU_TRY(h, cudaMalloc(&h->d_hyp, (size_t)npx * 10));                  // valid u8 | idepth f32 | var f32 | valid_out u8
+        CU_TRY(h, cudaMalloc(&h->d_nvalid, (size_t)h->cfg.max_keyframes * sizeof(int)));
+    }
+    int rc = guard_slot_write(h, h->kf_reader[slot]);
+    if (rc) return rc;
+    // the staging buffer is shared by all slots: the previous call's kernels (compute stream) must be done with it
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    uint8_t* d_valid = h->d_hyp + 8 * npx;
+    float* d_idepth = reinterpret_cast<float*>(h->d_hyp);
+    float* d_vars = d_idepth + npx;
+    uint8_t* d_vout = d_valid + npx;
+    CU_TRY(h, cudaMemcpyAsync(h->kf_img + (int64_t)slot * h->geo.img_off[kLevels], image, (size_t)h->geo.img_off[1], cudaMemcpyHostToDevice, h->copy_stream));
+    CU_TRY(h, cudaMemcpyAsync(d_valid, valid, (size_t)npx, cudaMemcpyHostToDevice, h->copy_stream));
+    CU_TRY(h, cudaMemcpyAsync(d_idepth, inv_depth_smoothed, (size_t)npx * 4, cudaMemcpyHostToDevice, h->copy_stream));
+    CU_TRY(h, cudaMemcpyAsync(d_vars, variance_smoothed, (size_t)npx * 4, cudaMemcpyHostToDevice, h->copy_stream));
+    rc = after_upload(h);
+    if (rc) return rc;
+    CU_TRY(h, cudaStreamWaitEvent(h->stream, h->up_ev, 0));
+    CU_TRY(h, cudaMemsetAsync(h->d_nvalid + slot, 0, sizeof(int), h->stream));
+    h->launches += launch_depth_pyramid(h->stream, d_valid, d_idepth, d_vars, h->kf_depth + slot * win, h->kf_var + slot * win,
+                                        valid_out ? d_vout : nullptr, h->d_nvalid + slot, h->geo);
+    CU_TRY(h, cudaGetLastError());
+    if (valid_out) {
+        CU_TRY(h, cudaMemcpyAsync(valid_out, d_vout, (size_t)npx, cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+    }
+    h->kf_nvalid[slot] = -2;                               // on the device, not fetched yet
+    h->kf_state[slot] = 1;
+    h->kf_lc_ready[slot] = 0;
+    h->kf_dirty.push_back(slot);
+    return ELLC_OK;
+}
+
+int ellc_read_keyframe_occupancy(ellc_handle* h, int32_t slot, int32_t* n_valid, float* occupancy) {
+    if (!h) return ELLC_ERR_INVALID;
+    if (slot < 0 || slot >= h->cfg.max_keyframes) { h->err = "bad keyframe slot"; return ELLC_ERR_INVALID; }
+    if (h->kf_nvalid[slot] == -1) { h->err = "keyframe slot was not uploaded from hypotheses"; return ELLC_ERR_NOT_READY; }
+    CU_TRY(h, cudaSetDevice(h->cfg.device));
+    if (h->kf_nvalid[slot] == -2) {
+        int v = 0;
+        CU_TRY(h, cudaMemcpyAsync(&v, h->d_nvalid + slot, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+        h->kf_nvalid[slot] = v;
+    }
+    if (n_valid) *n_valid = h->kf_nvalid[slot];
+    // depthMap::calculate_no_of_Seeds, src/DepthPropagation.cpp:1804-1830: float count / int(W*H) * 100
+    if (occupancy) *occupancy = (float)h->kf_nvalid[slot] / (h->geo.width * h->geo.height) * 100;
+    return ELLC_OK;
+}
+
+int ellc_read_keyframe_depth(ellc_handle* h, int32_t slot, int32_t level, float* depth, float* var) {
+    if (!h) return ELLC_ERR_INVALID;
+    if (slot < 0 || slot >= h->cfg.max_keyframes || level < 0 || level >= kLevels) { h->err = "bad slot/level"; return ELLC_ERR_INVALID; }
+    if (h->kf_state[slot] == 0) { h->err = "keyframe slot empty"; return ELLC_ERR_NOT_READY; }
+    CU_TRY(h, cudaSetDevice(h->cfg.device));
+    CU_TRY(h, cudaStreamSynchronize(h->copy_stream));
+    const int64_t win = h->geo.win_off[kLevels];
+    const size_t bytes = (size_t)(h->geo.win_off[level + 1] - h->geo.win_off[level]) * sizeof(float);
+    if (depth) CU_TRY(h, cudaMemcpyAsync(depth, h->kf_depth + slot * win + h->geo.win_off[level], bytes, cudaMemcpyDeviceToHost, h->stream));
+    if (var) CU_TRY(h, cudaMemcpyAsync(var, h->kf_var + slot * win + h->geo.win_off[level], bytes, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return ELLC_OK;
 }
 
 int ellc_frame_image_devptr(ellc_handle* h, int32_t slot, uint8_t** image) {

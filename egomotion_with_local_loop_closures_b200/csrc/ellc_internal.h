@@ -14,6 +14,10 @@ int launch_select(cudaStream_t st, const float* depth_pool, const float* var_poo
                   int* rowoff_pool, int* count_pool, SelGeo* geo_pool, SelPix* pix_pool, float* ikf_pool, const LevelK* K,
                   const int* d_slots, int n, const Geometry& geo);
 
+// keyframe depth / variance pyramids from hypotheses (src/DepthPropagation.cpp:1254-1306, :1637-1719); depth_slot / var_slot are
+// the keyframe slot's bases in the win layout; *d_n_valid (pre-zeroed) receives the number of valid hypotheses
+int launch_depth_pyramid(cudaStream_t st, const uint8_t* d_valid, const float* d_idepth, const float* d_var_s, float* depth_slot,
+                         float* var_slot, uint8_t* d_valid_out, int* d_n_valid, const Geometry& geo);
 // keyframe weight pyramid (src/PixelWisePyramid.cpp:546-548, src/Frame.cpp:678-695) and loop-closure records (:561-680, :938)
 int launch_accumulate_weights(cudaStream_t st, float* kf_weight_slot, const uint8_t* mask_slot, const float* frw_pool,
                               int64_t win, const int* d_frame_slots, int n);

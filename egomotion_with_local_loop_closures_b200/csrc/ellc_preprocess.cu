@@ -440,6 +440,59 @@ lc_prepare_kernel(const SelGeo* __restrict__ geo_pool, const SelPix* __restrict_
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Keyframe depth / variance pyramids from the depth module's per-pixel hypotheses: the step right before
+// the tracker, so that a keyframe costs one 9-byte-per-pixel upload instead of two 4-level f32 pyramids.
+// ------------------------------------------------------------------------------------------------------------------
+// depthMap::updateDepthImage, src/DepthPropagation.cpp:1273-1300, fused with calculate_no_of_Seeds (:1804-1830, counted on the
+// flags as they arrive).  Level 0 in the Mat convention (depth 0 = invalid, variance -1): buildInvVarDepth only reads a depth
+// where the variance is positive, so it sees the same values as in the reference's -1 array.
+__global__ void __launch_bounds__(256)
+depth_from_hypotheses_kernel(const uint8_t* __restrict__ valid, const float* __restrict__ idepth, const float* __restrict__ var_s,
+                             float* __restrict__ depth0, float* __restrict__ var0, uint8_t* __restrict__ valid_out,
+                             int* __restrict__ n_valid, int w, int h) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool v = false;
+    if (i < w * h) {
+        const int y = i / w, x = i - y * w;
+        v = valid[i] != 0;
+        const bool inner = !(y < 3 || y >= h - 3 || x < 3 || x >= w - 3);
+        const bool keep = v && inner;
+        const float id = idepth[i];
+        if (keep && id >= -0.05f) { depth0[i] = __fdiv_rn(1.0f, id); var0[i] = var_s[i]; }
+        else { depth0[i] = 0.0f; var0[i] = -1.0f; }
+        if (valid_out) valid_out[i] = keep ? 1 : 0;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && bal) atomicAdd(n_valid, __popc(bal));
+}
+
+// depthMap::buildInvVarDepth, src/DepthPropagation.cpp:1637-1719: one level from the previous one; the four children are
+// accumulated in the reference's order with individually rounded fp32 operations.
+__global__ void __launch_bounds__(256)
+build_inv_var_depth_kernel(const float* __restrict__ ds, const float* __restrict__ vs, float* __restrict__ dd, float* __restrict__ vd,
+                           int width, int height) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= width * height) return;
+    const int y = i / width, x = i - y * width, sw = 2 * width;
+    const int idx = 2 * (x + y * sw);
+    const int off[4] = {0, 1, sw, sw + 1};
+    float idepth_sum = 0.f, ivar_sum = 0.f;
+    int num = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float var = vs[idx + off[k]];
+        if (var > 0) {
+            const float ivar = __fdiv_rn(1.0f, var);
+            ivar_sum = __fadd_rn(ivar_sum, ivar);
+            idepth_sum = __fadd_rn(idepth_sum, __fdiv_rn(__fmul_rn(ivar, 1.0f), ds[idx + off[k]]));   // ivar * 1.0f / depth
+            ++num;
+        }
+    }
+    if (num > 0) { dd[i] = __fdiv_rn(ivar_sum, idepth_sum); vd[i] = __fdiv_rn((float)num, ivar_sum); }
+    else { dd[i] = 0.0f; vd[i] = -1.0f; }
+}
+
 // Small host payloads (slot lists, pair lists, schedules) are pulled from the pinned staging arena by the SMs instead of
 // the copy engine: a cudaMemcpyAsync on the compute stream would queue in the one H2D engine behind the bulk image /
 // depth uploads of the NEXT batch (copy stream) and stall this batch's kernels for the whole upload burst.
@@ -507,6 +560,19 @@ int launch_select(cudaStream_t st, const float* depth_pool, const float* var_poo
                                                                 img_slot_stride, rowoff_pool, rows_total, geo_pool,
                                                                 pix_pool, ikf_pool, ks, d_slots, geo);
     return 3;
+}
+
+int launch_depth_pyramid(cudaStream_t st, const uint8_t* d_valid, const float* d_idepth, const float* d_var_s, float* depth_slot,
+                         float* var_slot, uint8_t* d_valid_out, int* d_n_valid, const Geometry& geo) {
+    const int w = geo.width, h = geo.height;
+    depth_from_hypotheses_kernel<<<(w * h + 255) / 256, 256, 0, st>>>(d_valid, d_idepth, d_var_s, depth_slot, var_slot, d_valid_out, d_n_valid, w, h);
+    for (int l = 1; l < kLevels; ++l) {
+        const int n = geo.cols[l] * geo.rows[l];
+        build_inv_var_depth_kernel<<<(n + 255) / 256, 256, 0, st>>>(depth_slot + geo.win_off[l - 1], var_slot + geo.win_off[l - 1],
+                                                                    depth_slot + geo.win_off[l], var_slot + geo.win_off[l],
+                                                                    geo.cols[l], geo.rows[l]);
+    }
+    return kLevels;
 }
 
 int launch_accumulate_weights(cudaStream_t st, float* kf_weight_slot, const uint8_t* mask_slot, const float* frw_pool,

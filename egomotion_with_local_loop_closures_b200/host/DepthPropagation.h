@@ -7,9 +7,23 @@
 #include "ExternVariable.h"
 #include "Frame.h"
 
+// The members of the reference's depthhypothesis (src/DepthHypothesis.h) that updateDepthImage / calculate_no_of_Seeds read.
+struct depthhypothesis {
+    bool isValid;
+    float invDepthSmoothed;
+    float varianceSmoothed;
+    depthhypothesis() : isValid(false), invDepthSmoothed(-1.0f), varianceSmoothed(-1.0f) {}
+};
+
 class depthMap {
 public:
     depthMap();
+    depthhypothesis* currentDepthHypothesis;              // ORIG_COLS x ORIG_ROWS, filled by the caller's depth module
+    // src/DepthPropagation.cpp:1254-1315 (+ buildInvVarDepth :1637-1719, mapDepthArr2Mat :1721-1746) on the B200: uploads the
+    // hypotheses, builds the keyframe's depth / variance pyramids there, and mirrors them (and the border-invalidated isValid
+    // flags) back into keyFrame->depth, keyFrame->depth_pyramid[], deptharrptr[], depthvararrptr[].
+    void updateDepthImage(bool fromKeyFrameCreation = false);
+    float calculate_no_of_Seeds(bool calculate_on_current = true);      // :1804-1830
     frame* keyFrame;
     frame* currentFrame;
     float* deptharrptr[util::MAX_PYRAMID_LEVEL];          // stride ORIG_COLS >> level; level 0 uses -1 for invalid
@@ -21,4 +35,5 @@ public:
 
 private:
     std::vector<float> depth_store_[util::MAX_PYRAMID_LEVEL], var_store_[util::MAX_PYRAMID_LEVEL];
+    std::vector<depthhypothesis> hyp_store_;
 };

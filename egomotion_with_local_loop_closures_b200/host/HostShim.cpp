@@ -226,6 +226,8 @@ void frame::calculatePoseWrtWorld(frame* prev_image, float* d, bool frmhomo) {
 
 // ---- depthMap -----------------------------------------------------------------------------------------------------------
 depthMap::depthMap() : keyFrame(nullptr), currentFrame(nullptr), stamp(1) {
+    hyp_store_.assign((size_t)util::ORIG_COLS * util::ORIG_ROWS, depthhypothesis());
+    currentDepthHypothesis = hyp_store_.data();
     for (int l = 0; l < util::MAX_PYRAMID_LEVEL; ++l) {
         const size_t n = (size_t)(util::ORIG_COLS >> l) * (util::ORIG_ROWS >> l);
         depth_store_[l].assign(n, l == 0 ? -1.0f : 0.0f);
@@ -233,6 +235,48 @@ depthMap::depthMap() : keyFrame(nullptr), currentFrame(nullptr), stamp(1) {
         deptharrptr[l] = depth_store_[l].data();
         depthvararrptr[l] = var_store_[l].data();
     }
+}
+
+void depthMap::updateDepthImage(bool /*fromKeyFrameCreation*/) {
+    const int w = util::ORIG_COLS, h = util::ORIG_ROWS;
+    const size_t n = (size_t)w * h;
+    std::vector<unsigned char> valid(n), vout(n);
+    std::vector<float> idep(n), vs(n);
+    for (size_t i = 0; i < n; ++i) {
+        valid[i] = currentDepthHypothesis[i].isValid ? 1 : 0;
+        idep[i] = currentDepthHypothesis[i].invDepthSmoothed;
+        vs[i] = currentDepthHypothesis[i].varianceSmoothed;
+    }
+    std::lock_guard<std::mutex> lk(g.mu);
+    ellc_handle* hd = ctx();
+    frame* f = keyFrame;
+    int s = f->gpu_kf_slot;
+    if (s < 0 || g.kf_owner[s] != f) {                                       // same slot policy as keyframe_slot()
+        s = g.next_kf;
+        g.next_kf = (g.next_kf + 1) % kKfSlots;
+        if (g.kf_owner[s]) { g.kf_owner[s]->gpu_kf_slot = -1; g.kf_owner[s]->gpu_lc_ready = false; }
+        g.kf_owner[s] = f; f->gpu_kf_slot = s; f->gpu_lc_ready = false;
+        if (ellc_reset_keyframe_weights(hd, s) != ELLC_OK) fail("ellc_reset_keyframe_weights");
+    }
+    if (ellc_upload_keyframe_hypotheses(hd, s, f->image.ptr<uchar>(0), valid.data(), idep.data(), vs.data(), vout.data()) != ELLC_OK)
+        fail("ellc_upload_keyframe_hypotheses");
+    for (size_t i = 0; i < n; ++i) currentDepthHypothesis[i].isValid = vout[i] != 0;       // :1279-1282
+    for (int l = 0; l < util::MAX_PYRAMID_LEVEL; ++l) {
+        if (ellc_read_keyframe_depth(hd, s, l, f->depth_pyramid[l].ptr<float>(0), depthvararrptr[l]) != ELLC_OK) fail("ellc_read_keyframe_depth");
+        const size_t nl = (size_t)(w >> l) * (h >> l);
+        const float* d = f->depth_pyramid[l].ptr<float>(0);
+        for (size_t i = 0; i < nl; ++i) deptharrptr[l][i] = (l == 0 && depthvararrptr[0][i] < 0) ? -1.0f : d[i];   // deptharrpyr0 uses -1
+    }
+    std::memcpy(f->depth.ptr<float>(0), f->depth_pyramid[0].ptr<float>(0), n * sizeof(float));
+    ++stamp;
+    g.kf_stamp[s] = stamp;                                                   // the device copy IS the current one: no re-upload
+    if (f->gpu_lc_ready) { const int32_t ks = s; if (ellc_prepare_keyframes_lc(hd, 1, &ks) != ELLC_OK) fail("ellc_prepare_keyframes_lc"); }
+}
+
+float depthMap::calculate_no_of_Seeds(bool /*calculate_on_current*/) {
+    float count = 0;
+    for (int i = 0; i < util::ORIG_COLS * util::ORIG_ROWS; ++i) count += float(currentDepthHypothesis[i].isValid);
+    return count / (util::ORIG_COLS * util::ORIG_ROWS) * 100;
 }
 
 // ---- PixelWisePyramid ---------------------------------------------------------------------------------------------------

@@ -132,6 +132,19 @@ int ellc_upload_keyframe(ellc_handle* h, int32_t kf_slot, const uint8_t* image,
  * Raw device pointers into a slot, for callers that already hold the data on the GPU (cudaMemcpyAsync D2D, another
  * kernel, ...).  After writing, call ellc_prepare_* for the touched slots.  level_offsets (ELLC_LEVELS+1 entries,
  * in elements) describe how the depth / var levels are concatenated. */
+/* Keyframe from the depth module's hypotheses instead of ready-made pyramids: replaces
+ * depthMap::updateDepthImage + buildInvVarDepth + mapDepthArr2Mat (src/DepthPropagation.cpp:1254-1315, :1637-1746).  valid /
+ * inv_depth_smoothed / variance_smoothed are the isValid / invDepthSmoothed / varianceSmoothed members of the width x height
+ * depthhypothesis array as SoA.  The 3-pixel border is invalidated as the reference does; valid_out (may be NULL) receives the
+ * updated flags.  Depth / variance pyramids are built on the device (bit-identical to the reference's fp32 sequence). */
+int ellc_upload_keyframe_hypotheses(ellc_handle* h, int32_t slot, const uint8_t* image, const uint8_t* valid,
+                                    const float* inv_depth_smoothed, const float* variance_smoothed, uint8_t* valid_out);
+/* depthMap::calculate_no_of_Seeds (src/DepthPropagation.cpp:1804-1830) on the flags passed to the last
+ * ellc_upload_keyframe_hypotheses of this slot: the depthMapOccupancy column of poses_orig.txt (src/main.cpp:361,373). */
+int ellc_read_keyframe_occupancy(ellc_handle* h, int32_t slot, int32_t* n_valid, float* occupancy);
+/* depth_pyramid[level] (0 = invalid) and depthvararrptr[level] (-1 = invalid) as resident on the device. */
+int ellc_read_keyframe_depth(ellc_handle* h, int32_t slot, int32_t level, float* depth, float* var);
+
 int ellc_frame_image_devptr(ellc_handle* h, int32_t frame_slot, uint8_t** image);
 int ellc_keyframe_devptrs(ellc_handle* h, int32_t kf_slot, uint8_t** image, float** depth, float** var,
                           int64_t level_offsets[ELLC_LEVELS + 1]);

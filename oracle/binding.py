@@ -149,6 +149,24 @@ def build_depth_pyramid(depth0_arr, var0):
     return d, v
 
 
+def update_depth_image(valid, inv_depth_smoothed, variance_smoothed):
+    """Level-0 depth image / arrays from per-pixel hypotheses + the 4-level pyramids (updateDepthImage -> buildInvVarDepth ->
+    mapDepthArr2Mat).  Returns dict(valid_out, depth [4 levels, Mat convention: 0 = invalid], var [4 levels, -1 = invalid],
+    n_valid, occupancy)."""
+    valid = np.ascontiguousarray(valid, np.uint8).copy()
+    h, w = valid.shape
+    idep = np.ascontiguousarray(inv_depth_smoothed, np.float32)
+    vs = np.ascontiguousarray(variance_smoothed, np.float32)
+    dmat = np.zeros((h, w), np.float32); darr = np.zeros((h, w), np.float32); varr = np.zeros((h, w), np.float32)
+    occ = C.c_float()
+    _l = lib()
+    _l.ellc_oracle_update_depth_image.restype = C.c_int
+    n = _l.ellc_oracle_update_depth_image(w, h, _p(valid), _p(idep), _p(vs), _p(dmat), _p(darr), _p(varr), C.byref(occ))
+    d, v = build_depth_pyramid(darr, varr)
+    d[0] = dmat                                             # mapDepthArr2Mat: depth_pyramid[0] = keyFrame->depth
+    return dict(valid_out=valid, depth=d, var=v, n_valid=n, occupancy=occ.value)
+
+
 def se3_exp(pose):
     T = np.empty(16, np.float32)
     lib().ellc_oracle_se3_exp(_p(_f6(pose)), _p(T))

@@ -734,6 +734,30 @@ void ellc_oracle_build_depth_pyramid(int w, int h, float* const* depth, float* c
     }
 }
 
+int ellc_oracle_update_depth_image(int w, int h, uint8_t* valid, const float* idepth, const float* var_s,
+                                   float* depth_mat, float* depth_arr, float* var_arr, float* occupancy) {
+    // depthMap::calculate_no_of_Seeds, src/DepthPropagation.cpp:1804-1830 (float counter, /(W*H)*100)
+    float count = 0;
+    for (int i = 0; i < w * h; ++i) count += float(valid[i] != 0);
+    if (occupancy) *occupancy = count / (w * h) * 100;
+    // src/DepthPropagation.cpp:1273-1300
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            const int i = x + y * w;
+            if (y < 3 || y >= h - 3 || x < 3 || x >= w - 3) valid[i] = 0;
+            if (valid[i] && idepth[i] >= -0.05f) {
+                depth_mat[i] = (1 / idepth[i]);
+                depth_arr[i] = (1 / idepth[i]);
+                var_arr[i] = var_s[i];
+            } else {
+                depth_mat[i] = 0.0f;
+                depth_arr[i] = -1.0f;
+                var_arr[i] = -1.0f;
+            }
+        }
+    return (int)count;
+}
+
 void ellc_oracle_se3_exp(const float pose[6], float T[16]) {
     M4 r = mat_exp_f32(se3_hat(pose));
     std::memcpy(T, r.a, sizeof(r.a));

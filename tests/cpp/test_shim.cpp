@@ -61,6 +61,26 @@ int main(int argc, char** argv) {
         // constant-weight loop-closure flow (FLAG_DO_CONST_WEIGHT_POSE_ESTIMATION): sequential tracks save their weights
         // (src/ImageFunc.cpp:280-288), the keyframe is finalised (src/main.cpp:431-434), then a loop-closure pair runs the
         // inverse-compositional tracker (src/ImageFunc.cpp:241-244)
+        // keyframe from depth hypotheses (depthMap::updateDepthImage on the device): rebuild the same depth from 1/depth hypotheses
+        {
+            frame kf2(kf.image.ptr<unsigned char>(0), w, h);
+            depthMap dm2;
+            dm2.keyFrame = &kf2;
+            const float* d0 = kf.depth_pyramid[0].ptr<float>(0);
+            for (int i = 0; i < w * h; ++i) {
+                dm2.currentDepthHypothesis[i].isValid = d0[i] > 0;
+                dm2.currentDepthHypothesis[i].invDepthSmoothed = d0[i] > 0 ? 1.0f / d0[i] : -1.0f;
+                dm2.currentDepthHypothesis[i].varianceSmoothed = dm.depthvararrptr[0][i];
+            }
+            const float occ_in = dm2.calculate_no_of_Seeds();
+            dm2.updateDepthImage();
+            int c1 = 0, c3 = 0;
+            for (int i = 0; i < (w >> 1) * (h >> 1); ++i) c1 += kf2.depth_pyramid[1].ptr<float>(0)[i] > 0;
+            for (int i = 0; i < (w >> 3) * (h >> 3); ++i) c3 += kf2.depth_pyramid[3].ptr<float>(0)[i] > 0;
+            float init[6] = {0, 0, 0, 0, 0, 0};
+            std::vector<float> p = GetImagePoseEstimate(&kf2, frames[0], 2, &dm2, &kf2, init);
+            printf("hyp %.9g %.9g %d %d %.9g %.9g %.9g\n", occ_in, dm2.calculate_no_of_Seeds(), c1, c3, p[0], p[1], p[2]);
+        }
         util::FLAG_DO_CONST_WEIGHT_POSE_ESTIMATION = true;
         prev = &kf;
         for (int i = 0; i < n; ++i) {

@@ -83,6 +83,16 @@ def test_shim_tracks_like_the_reference_driver(tmp_path, oracle_mod):
         assert abs(float(g[11]) - o["res_sum_f64"]) <= 1e-5 * o["res_sum_f64"]
         assert abs(float(g[13]) - o["H_f64"][0, 0]) <= 1e-5 * o["H_f64"][0, 0]
     assert [l for l in lines if l[0] == "count2"][0][1] == str(int((kf["depth"][2] > 0).sum()))
+    # keyframe rebuilt from 1/depth hypotheses through depthMap::updateDepthImage (device pyramids)
+    d0 = kf["depth"][0]
+    with np.errstate(divide="ignore"):
+        ref = oracle_mod.update_depth_image((d0 > 0).astype(np.uint8), np.where(d0 > 0, np.float32(1) / d0, np.float32(-1)).astype(np.float32), kf["var"][0])
+    hyp = [l for l in lines if l[0] == "hyp"][0]
+    assert abs(float(hyp[1]) - ref["occupancy"]) < 1e-4
+    assert abs(float(hyp[2]) - 100.0 * float((ref["valid_out"] != 0).sum()) / (w * h)) < 1e-3
+    assert int(hyp[3]) == int((ref["depth"][1] > 0).sum()) and int(hyp[4]) == int((ref["depth"][3] > 0).sum())
+    opose, _ = oracle_mod.track(ocfg, kf["image"], frames[0], ref["depth"], ref["var"], np.zeros(6, np.float32))
+    assert np.abs(np.array(hyp[5:8], np.float64) - opose[:3]).max() < 2e-6
     # constant-weight loop-closure flow: weights saved by the sequential tracks, finalised, then one loop-closure pair
     h_, w_ = h, w
     wp = [np.zeros((h_ >> l, w_ >> l), np.float32) for l in range(4)]

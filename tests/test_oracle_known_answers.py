@@ -96,3 +96,26 @@ def test_oracle_summation_order_envelope(oracle_mod, scene_vga):
     print(f"band-count envelope: pose {worst_pose:.2e}, residual sums {worst_res:.2e}")
     assert worst_pose < 1e-5 and worst_res < 1e-4
     assert worst_res > 1e-8          # it is genuinely order-dependent
+
+
+def test_depth_image_from_hypotheses_known_answers(oracle_mod):
+    """updateDepthImage / buildInvVarDepth / calculate_no_of_Seeds (src/DepthPropagation.cpp:1254-1306, :1637-1719, :1804-1830)."""
+    h, w = 16, 24
+    valid = np.ones((h, w), np.uint8)
+    idep = np.full((h, w), 0.5, np.float32)
+    var = np.full((h, w), 0.04, np.float32)
+    idep[8, 8] = -0.2                                   # below -0.05: dropped although flagged valid
+    valid[9, 9] = 0
+    r = oracle_mod.update_depth_image(valid, idep, var)
+    assert r["n_valid"] == h * w - 1 and abs(r["occupancy"] - 100.0 * (h * w - 1) / (h * w)) < 1e-4
+    inner = np.zeros((h, w), bool); inner[3:-3, 3:-3] = True
+    assert np.array_equal(r["valid_out"] != 0, inner & (valid != 0))        # the 3-pixel border is invalidated (:1279-1282)
+    d0, v0 = r["depth"][0], r["var"][0]
+    keep = inner.copy(); keep[8, 8] = False; keep[9, 9] = False
+    assert np.all(d0[keep] == 2.0) and np.all(d0[~keep] == 0.0) and np.all(v0[keep] == np.float32(0.04)) and np.all(v0[~keep] == -1.0)
+    # level 1: a cell with four valid children keeps depth 2 and variance 0.04; cells with no valid child are (0, -1)
+    d1, v1 = r["depth"][1], r["var"][1]
+    assert d1[3, 3] == 2.0 and abs(v1[3, 3] - 0.04) < 1e-7 and d1[0, 0] == 0.0 and v1[0, 0] == -1.0
+    # cell (4, 4) has three valid children ((8,8) and (9,9) dropped): variance = num / sum(1/var) stays 0.04, depth stays 2
+    assert d1[4, 4] == 2.0 and abs(v1[4, 4] - 0.04) < 1e-7
+
