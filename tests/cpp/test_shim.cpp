@@ -4,6 +4,9 @@
 // 4 variance levels; n_frames u8 images.  Prints one line per result; the pytest side compares with the CPU oracle.
 #include <cstdio>
 #include <cstdlib>
+#include <fstream>
+#include <sstream>
+#include <string>
 #include <vector>
 
 #include "DepthPropagation.h"
@@ -11,11 +14,35 @@
 #include "Frame.h"
 #include "ImageFunc.h"
 #include "PixelWisePyramid.h"
+#include "PoseFiles.h"
 
 static void rd(FILE* f, void* p, size_t n) { if (fread(p, 1, n, f) != n) { fprintf(stderr, "short read\n"); exit(2); } }
 
 int main(int argc, char** argv) {
     if (argc < 2) { fprintf(stderr, "usage: test_shim blob [--link-only]\n"); return 2; }
+    if (argc > 2 && std::string(argv[2]) == "--posefiles") {
+        // host-only: the text files the reference's callers write (no GPU involved)
+        util::BATCH_START_ID = 101;
+        frame kf, f;
+        kf.frameId = 1; kf.rescaleFactor = 0.98765432f;
+        f.frameId = 7;
+        const float w[6] = {0.0123456789f, -1.5e-5f, 3.0f, 123456.789f, -0.000123456f, 1e-10f};
+        for (int i = 0; i < 6; ++i) { f.poseWrtWorld[i] = w[i]; f.poseWrtOrigin[i] = -w[5 - i]; }
+        std::ofstream o1(std::string(argv[1]) + ".orig"), o2(std::string(argv[1]) + ".match");
+        ellc_host::write_orig_pose(o1, &f, &kf, 37.123456f);
+        ellc_host::write_match_pose(o2, &f, &kf, 37.123456f);
+        ellc_host::write_match_pose(o2, &f, &kf, 12.5f, 0.0712345f, 9.87654321f, 4.5f);
+        o1.close(); o2.close();
+        std::ifstream in(std::string(argv[1]) + ".orig");
+        int id, kid; float p[6];
+        in >> id; in.seekg(0);
+        std::ifstream init(std::string(argv[1]) + ".orig");
+        int fn; init >> fn >> kid;                       // skip the two ids, then read six floats back
+        std::stringstream ss; ss << fn << " "; for (int i = 0; i < 6; ++i) { float v; init >> v; ss << v << " "; }
+        int fno; const bool ok = ellc_host::read_initial_pose(ss, fno, p);
+        printf("posefiles ok %d %d %.9g\n", ok ? 1 : 0, fno, p[3]);
+        return 0;
+    }
     if (argc > 2) { printf("link ok\n"); return 0; }
     FILE* f = fopen(argv[1], "rb");
     if (!f) return 2;

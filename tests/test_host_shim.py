@@ -14,7 +14,8 @@ EXE = os.path.join(ROOT, "tests", "cpp", "test_shim")
 def build_shim():
     import __graft_entry__ as g
     g.build()
-    src = [os.path.join(ROOT, "tests", "cpp", "test_shim.cpp"), os.path.join(PKG, "host", "HostShim.cpp")]
+    src = [os.path.join(ROOT, "tests", "cpp", "test_shim.cpp"), os.path.join(PKG, "host", "HostShim.cpp"),
+           os.path.join(PKG, "host", "PoseFiles.cpp")]
     deps = src + [os.path.join(PKG, "libellc_gn.so")]
     if not os.path.exists(EXE) or any(os.path.getmtime(s) > os.path.getmtime(EXE) for s in deps):
         subprocess.check_call(["g++", "-std=c++11", "-O2", "-pthread", "-I", os.path.join(PKG, "host"), "-o", EXE] + src +
@@ -26,6 +27,27 @@ def test_shim_builds_and_links():
     exe = build_shim()
     out = subprocess.check_output([exe, "none", "--link-only"], text=True)
     assert "link ok" in out
+
+
+def test_pose_files_match_the_reference_format(tmp_path):
+    """poses_orig.txt / matchframes*.txt (src/main.cpp:373,382; src/GlobalOptimize.cpp:580): the C++ writers use the reference's own
+    stream expressions; the Python writers must produce the same bytes, and the files must parse back."""
+    from egomotion_with_local_loop_closures_b200 import posefiles
+    exe = build_shim()
+    base = str(tmp_path / "poses")
+    out = subprocess.check_output([exe, base, "--posefiles"], text=True)
+    assert out.startswith("posefiles ok 1 107")
+    w = np.array([0.0123456789, -1.5e-5, 3.0, 123456.789, -0.000123456, 1e-10], np.float32)
+    o = -w[::-1]
+    orig = open(base + ".orig").read()
+    match = open(base + ".match").read().splitlines(keepends=True)
+    assert orig == posefiles.orig_pose_line(7, 1, w, 0.98765432, 37.123456, batch_start_id=101)
+    assert orig.split()[:4] == ["107", "101", "0.0123457", "-1.5e-05"]                  # 6 significant digits, ids offset by BATCH_START_ID-1
+    assert match[0] == posefiles.match_pose_line(7, 1, o, 0.98765432, 37.123456, batch_start_id=101)
+    assert match[1] == posefiles.match_pose_line(7, 1, o, 0.98765432, 12.5, 0.0712345, 9.87654321, 4.5, batch_start_id=101)
+    assert match[0].rstrip().endswith(" 0 0 0")
+    rows = posefiles.read_pose_file(base + ".match")
+    assert rows.shape == (2, 13) and rows[1, 10] == pytest.approx(0.0712345, rel=1e-5)
 
 
 @pytest.mark.gpu
