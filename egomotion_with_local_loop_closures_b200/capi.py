@@ -56,6 +56,9 @@ RESULT_DTYPE = np.dtype([("pose", "<f4", 6), ("H", "<f4", 21), ("b", "<f4", 6), 
 TRACE_DTYPE = np.dtype([("H", "<f4", 36), ("b", "<f4", 6), ("delta", "<f4", 6), ("weighted_pose", "<f4"),
                         ("pose_after", "<f4", 6), ("res_sum", "<f4"), ("weight_sum", "<f4"), ("n_oob", "<i4"),
                         ("executed", "<i4"), ("pad", "<i4", 5)])
+LC_CAND_DTYPE = np.dtype([("loop_frame_slot", "<i4"), ("test_frame_slot", "<i4"), ("loop_pose_world", "<f4", 6), ("test_pose_world", "<f4", 6)])
+LC_STATS_DTYPE = np.dtype([("match_value", "<f8"), ("rms_error", "<f4"), ("relative_view_angle", "<f4"), ("pass", "<i4"), ("reserved", "<i4")])
+assert LC_CAND_DTYPE.itemsize == 56 and LC_STATS_DTYPE.itemsize == 24
 assert PAIR_DTYPE.itemsize == 36 and RESULT_DTYPE.itemsize == 256 and TRACE_DTYPE.itemsize == 256
 
 # every symbol include/ellc_gn.h declares
@@ -67,7 +70,7 @@ SYMBOLS = ["ellc_default_config", "ellc_create", "ellc_destroy", "ellc_last_erro
            "ellc_read_keyframe_level", "ellc_level_dims", "ellc_concat_relative", "ellc_concat_origin",
            "ellc_se3_exp", "ellc_launch_count", "ellc_reset_launch_count", "ellc_stream", "ellc_stream_of", "ellc_selftest_division", "ellc_reset_keyframe_weights", "ellc_accumulate_weights",
            "ellc_finalise_weights", "ellc_upload_keyframe_weights", "ellc_read_keyframe_weights", "ellc_read_frame_weights",
-           "ellc_prepare_keyframes_lc", "ellc_upload_keyframe_hypotheses", "ellc_read_keyframe_occupancy", "ellc_read_keyframe_depth", "ellc_last_track_kernel_ms"]
+           "ellc_prepare_keyframes_lc", "ellc_frame_histograms", "ellc_lc_gate", "ellc_upload_keyframe_hypotheses", "ellc_read_keyframe_occupancy", "ellc_read_keyframe_depth", "ellc_last_track_kernel_ms"]
 
 _lib = None
 
@@ -119,6 +122,8 @@ def lib():
         L.ellc_upload_keyframe_hypotheses.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 5
         L.ellc_read_keyframe_occupancy.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_float)]
         L.ellc_read_keyframe_depth.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+        L.ellc_frame_histograms.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+        L.ellc_lc_gate.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_float, C.c_float, C.c_void_p]
         L.ellc_selftest_division.argtypes = [C.c_void_p, C.c_int64, C.c_uint64, C.POINTER(C.c_int64)]
         L.ellc_stream_of.restype = C.c_void_p
         L.ellc_stream_of.argtypes = [C.c_void_p, C.c_int32]
@@ -332,6 +337,23 @@ class Tracker:
         d, v = np.zeros(shape, np.float32), np.zeros(shape, np.float32)
         self._chk(lib().ellc_read_keyframe_depth(self._h, slot, level, _p(d), _p(v)))
         return d, v
+
+    # -- loop-closure candidate gating
+    def frame_histograms(self, frame_slots):
+        fs = np.ascontiguousarray(frame_slots, np.int32)
+        out = np.zeros((len(fs), 256), np.float32)
+        self._chk(lib().ellc_frame_histograms(self._h, len(fs), _p(fs), _p(out)))
+        return out
+
+    def lc_gate(self, loop_slots, test_slots, loop_poses, test_poses, match_threshold=0.1, max_rel_view_angle=10.0):
+        n = len(loop_slots)
+        cand = np.zeros(n, LC_CAND_DTYPE)
+        cand["loop_frame_slot"] = loop_slots; cand["test_frame_slot"] = test_slots
+        cand["loop_pose_world"] = np.asarray(loop_poses, np.float32).reshape(n, 6)
+        cand["test_pose_world"] = np.asarray(test_poses, np.float32).reshape(n, 6)
+        out = np.zeros(n, LC_STATS_DTYPE)
+        self._chk(lib().ellc_lc_gate(self._h, n, _p(cand), float(match_threshold), float(max_rel_view_angle), _p(out)))
+        return out
 
     # -- constant-weight loop-closure variant
     def reset_keyframe_weights(self, kf_slot):

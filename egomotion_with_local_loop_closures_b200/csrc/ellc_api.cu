@@ -42,6 +42,8 @@ struct ellc_handle {
     // pools
     uint8_t* fr_img; uint32_t* fr_tex;
     uint8_t* kf_img; float* kf_depth; float* kf_var; uint8_t* kf_mask; SelGeo* kf_geo; SelPix* kf_pix; float* kf_ikf;
+    float* fr_hist;                                    // [frame slot][256] normalised histograms (loop-closure gating), lazy
+    std::vector<char> fr_hist_ready;
     // hypothesis staging of ellc_upload_keyframe_hypotheses (allocated on first use) and per-slot valid counts
     uint8_t* d_hyp; int* d_nvalid;
     std::vector<int> kf_nvalid;                        // -1: not uploaded from hypotheses / not fetched yet
@@ -132,7 +134,7 @@ int ellc_destroy(ellc_handle* h) {
     if (h->d2h_stream) cudaStreamSynchronize(h->d2h_stream);
     cudaFree(h->fr_img); cudaFree(h->fr_tex); cudaFree(h->kf_img); cudaFree(h->kf_depth); cudaFree(h->kf_var);
     cudaFree(h->kf_mask); cudaFree(h->kf_geo); cudaFree(h->kf_pix); cudaFree(h->kf_ikf);
-    cudaFree(h->d_hyp); cudaFree(h->d_nvalid);
+    cudaFree(h->d_hyp); cudaFree(h->d_nvalid); cudaFree(h->fr_hist);
     cudaFree(h->fr_weight); cudaFree(h->kf_weight); cudaFree(h->kf_lc); cudaFree(h->kf_lcH); cudaFree(h->kf_count); cudaFree(h->kf_rowcount); cudaFree(h->kf_rowoff);
     cudaFree(h->d_slots); cudaFree(h->d_pairs); cudaFree(h->d_results2[0]); cudaFree(h->d_results2[1]); cudaFree(h->d_order); cudaFree(h->d_trace); cudaFree(h->d_small);
     cudaFree(h->d_weight);
@@ -199,6 +201,7 @@ int ellc_create(const ellc_config* cfg, ellc_handle** out) {
     h->kf_wcount.assign((size_t)cfg->max_keyframes * kLevels, 0);
     h->kf_lc_ready.assign(cfg->max_keyframes, 0);
     h->kf_nvalid.assign(cfg->max_keyframes, -1);
+    h->fr_hist_ready.assign(cfg->max_frames, 0);
     h->kf_reader.assign(cfg->max_keyframes, 0);
     const int64_t img = h->geo.img_off[kLevels], win = h->geo.win_off[kLevels];
     const int64_t nf = cfg->max_frames, nk = cfg->max_keyframes;
@@ -504,6 +507,7 @@ int ellc_upload_frame(ellc_handle* h, int32_t slot, const uint8_t* image) {
     CU_TRY(h, cudaMemcpyAsync(h->fr_img + (int64_t)slot * h->geo.img_off[kLevels], image, (size_t)h->geo.img_off[1],
                               cudaMemcpyHostToDevice, h->copy_stream));
     h->fr_state[slot] = 1;
+    h->fr_hist_ready[slot] = 0;
     h->fr_dirty.push_back(slot);
     return after_upload(h);
 }
@@ -600,6 +604,54 @@ int ellc_read_keyframe_depth(ellc_handle* h, int32_t slot, int32_t level, float*
     const size_t bytes = (size_t)(h->geo.win_off[level + 1] - h->geo.win_off[level]) * sizeof(float);
     if (depth) CU_TRY(h, cudaMemcpyAsync(depth, h->kf_depth + slot * win + h->geo.win_off[level], bytes, cudaMemcpyDeviceToHost, h->stream));
     if (var) CU_TRY(h, cudaMemcpyAsync(var, h->kf_var + slot * win + h->geo.win_off[level], bytes, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return ELLC_OK;
+}
+
+int ellc_frame_histograms(ellc_handle* h, int32_t n, const int32_t* frame_slots, float* hist) {
+    if (!h) return ELLC_ERR_INVALID;
+    if (n < 0 || (n > 0 && !frame_slots) || n > h->slots_cap) { h->err = "bad frame slot list"; return ELLC_ERR_INVALID; }
+    for (int i = 0; i < n; ++i) {
+        if (frame_slots[i] < 0 || frame_slots[i] >= h->cfg.max_frames) { h->err = "frame slot out of range"; return ELLC_ERR_INVALID; }
+        if (h->fr_state[frame_slots[i]] == 0) { h->err = "frame slot empty"; return ELLC_ERR_NOT_READY; }
+    }
+    if (n == 0) return ELLC_OK;
+    CU_TRY(h, cudaSetDevice(h->cfg.device));
+    if (!h->fr_hist) CU_TRY(h, cudaMalloc(&h->fr_hist, (size_t)h->cfg.max_frames * 256 * sizeof(float)));
+    if (h->uploads_pending) { CU_TRY(h, cudaStreamWaitEvent(h->stream, h->up_ev, 0)); }      // the level-0 images must have landed
+    int rc = stage_h2d(h, h->d_slots, frame_slots, (size_t)n * sizeof(int));
+    if (rc) return rc;
+    h->launches += launch_frame_histograms(h->stream, h->fr_img, h->geo.img_off[kLevels], h->d_slots, n, h->geo.width * h->geo.height, h->fr_hist);
+    CU_TRY(h, cudaGetLastError());
+    for (int i = 0; i < n; ++i) h->fr_hist_ready[frame_slots[i]] = 1;
+    if (hist) {
+        for (int i = 0; i < n; ++i)
+            CU_TRY(h, cudaMemcpyAsync(hist + (size_t)i * 256, h->fr_hist + (size_t)frame_slots[i] * 256, 256 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+    }
+    return ELLC_OK;
+}
+
+int ellc_lc_gate(ellc_handle* h, int32_t n, const ellc_lc_candidate* cand, float match_threshold, float max_rel_view_angle, ellc_lc_stats* stats) {
+    if (!h) return ELLC_ERR_INVALID;
+    if (n < 0 || (n > 0 && (!cand || !stats))) { h->err = "bad candidate list"; return ELLC_ERR_INVALID; }
+    for (int i = 0; i < n; ++i) {
+        const int a = cand[i].loop_frame_slot, b = cand[i].test_frame_slot;
+        if (a < 0 || a >= h->cfg.max_frames || b < 0 || b >= h->cfg.max_frames) { h->err = "candidate frame slot out of range"; return ELLC_ERR_INVALID; }
+        if (!h->fr_hist || !h->fr_hist_ready[a] || !h->fr_hist_ready[b]) { h->err = "candidate without histogram: call ellc_frame_histograms first"; return ELLC_ERR_NOT_READY; }
+    }
+    if (n == 0) return ELLC_OK;
+    CU_TRY(h, cudaSetDevice(h->cfg.device));
+    const size_t in_bytes = (size_t)n * sizeof(ellc_lc_candidate), out_bytes = (size_t)n * sizeof(ellc_lc_stats);
+    void* d_buf = nullptr;
+    CU_TRY(h, cudaMallocAsync(&d_buf, in_bytes + out_bytes, h->stream));
+    ellc_lc_candidate* d_cand = reinterpret_cast<ellc_lc_candidate*>(d_buf);
+    ellc_lc_stats* d_out = reinterpret_cast<ellc_lc_stats*>(reinterpret_cast<char*>(d_buf) + in_bytes);
+    CU_TRY(h, cudaMemcpyAsync(d_cand, cand, in_bytes, cudaMemcpyHostToDevice, h->stream));
+    h->launches += launch_lc_gate(h->stream, h->fr_hist, d_cand, n, match_threshold, max_rel_view_angle, d_out);
+    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaMemcpyAsync(stats, d_out, out_bytes, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaFreeAsync(d_buf, h->stream));
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     return ELLC_OK;
 }

@@ -14,6 +14,12 @@ int launch_select(cudaStream_t st, const float* depth_pool, const float* var_poo
                   int* rowoff_pool, int* count_pool, SelGeo* geo_pool, SelPix* pix_pool, float* ikf_pool, const LevelK* K,
                   const int* d_slots, int n, const Geometry& geo);
 
+// loop-closure gating: normalised 256-bin histograms of the level-0 images of n frame slots (hist_pool: [slot][256]) and the
+// per-candidate statistics (ellc_track.cu, next to the pose algebra)
+int launch_frame_histograms(cudaStream_t st, const uint8_t* img_pool, int64_t img_slot_stride, const int* d_slots, int n, int n_pixels,
+                            float* hist_pool);
+int launch_lc_gate(cudaStream_t st, const float* hist_pool, const ellc_lc_candidate* d_cand, int n, float match_threshold,
+                   float max_rel_view_angle, ellc_lc_stats* d_out);
 // keyframe depth / variance pyramids from hypotheses (src/DepthPropagation.cpp:1254-1306, :1637-1719); depth_slot / var_slot are
 // the keyframe slot's bases in the win layout; *d_n_valid (pre-zeroed) receives the number of valid hypotheses
 int launch_depth_pyramid(cudaStream_t st, const uint8_t* d_valid, const float* d_idepth, const float* d_var_s, float* depth_slot,

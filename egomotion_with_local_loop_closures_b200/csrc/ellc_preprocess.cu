@@ -493,6 +493,38 @@ build_inv_var_depth_kernel(const float* __restrict__ ds, const float* __restrict
     else { dd[i] = 0.0f; vd[i] = -1.0f; }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Loop-closure candidate gating: the per-frame histogram and the per-candidate statistics of
+// globalOptimize::findMatch; the ring / window bookkeeping around them stays with the caller.
+// ------------------------------------------------------------------------------------------------------------------
+// calculateImageHistogram, src/GlobalOptimize.cpp:40-100.  Counts are integers (exact in fp32 up to 2^24 pixels), so the
+// float sum and the normalisation are bit-identical to cv::calcHist + the reference's loops whatever the counting order.
+__global__ void __launch_bounds__(256)
+frame_histogram_kernel(const uint8_t* __restrict__ img_pool, int64_t img_slot_stride, const int* __restrict__ slots, int n_pixels,
+                       float* __restrict__ hist_pool) {
+    __shared__ unsigned s_cnt[256];
+    const int slot = slots[blockIdx.x];
+    const uint8_t* __restrict__ img = img_pool + (int64_t)slot * img_slot_stride;
+    s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int n4 = n_pixels >> 2;
+    for (int i = threadIdx.x; i < n4; i += 256) {
+        const uint32_t v = reinterpret_cast<const uint32_t*>(img)[i];
+        atomicAdd(&s_cnt[v & 0xff], 1u); atomicAdd(&s_cnt[(v >> 8) & 0xff], 1u);
+        atomicAdd(&s_cnt[(v >> 16) & 0xff], 1u); atomicAdd(&s_cnt[v >> 24], 1u);
+    }
+    for (int i = 4 * n4 + threadIdx.x; i < n_pixels; i += 256) atomicAdd(&s_cnt[img[i]], 1u);
+    __syncthreads();
+    __shared__ float s_sum;
+    if (threadIdx.x == 0) {
+        float sum = 0.f;
+        for (int i = 0; i < 256; ++i) sum = __fadd_rn(sum, (float)s_cnt[i]);      // :78-83, sequential
+        s_sum = sum;
+    }
+    __syncthreads();
+    hist_pool[(int64_t)slot * 256 + threadIdx.x] = __fdiv_rn((float)s_cnt[threadIdx.x], s_sum);   // :85-88
+}
+
 // Small host payloads (slot lists, pair lists, schedules) are pulled from the pinned staging arena by the SMs instead of
 // the copy engine: a cudaMemcpyAsync on the compute stream would queue in the one H2D engine behind the bulk image /
 // depth uploads of the NEXT batch (copy stream) and stall this batch's kernels for the whole upload burst.
@@ -573,6 +605,12 @@ int launch_depth_pyramid(cudaStream_t st, const uint8_t* d_valid, const float* d
                                                                     geo.cols[l], geo.rows[l]);
     }
     return kLevels;
+}
+
+int launch_frame_histograms(cudaStream_t st, const uint8_t* img_pool, int64_t img_slot_stride, const int* d_slots, int n, int n_pixels,
+                            float* hist_pool) {
+    frame_histogram_kernel<<<n, 256, 0, st>>>(img_pool, img_slot_stride, d_slots, n_pixels, hist_pool);
+    return 1;
 }
 
 int launch_accumulate_weights(cudaStream_t st, float* kf_weight_slot, const uint8_t* mask_slot, const float* frw_pool,

@@ -107,6 +107,21 @@ typedef struct ellc_iter_trace {
     int32_t pad[5];
 } ellc_iter_trace;                    /* 64 x 4 B */
 
+/* Loop-closure candidate gating (globalOptimize::findMatch, src/GlobalOptimize.cpp:274-452). */
+typedef struct ellc_lc_candidate {
+    int32_t loop_frame_slot;          /* loopFrameArray[i]: a frame slot whose histogram was computed                */
+    int32_t test_frame_slot;          /* currentLoopFrame                                                            */
+    float   loop_pose_world[6];       /* loopFrameArray[i].poseWrtWorld                                              */
+    float   test_pose_world[6];       /* currentLoopFrame.poseWrtWorld                                               */
+} ellc_lc_candidate;
+typedef struct ellc_lc_stats {
+    double  match_value;              /* compareHist(loop, test, CV_COMP_KL_DIV), :351                                */
+    float   rms_error;                /* calculateRotationStats, :426                                                 */
+    float   relative_view_angle;      /* degrees, :435-436                                                            */
+    int32_t pass;                     /* matchValue <= threshold && angle <= max angle, :364-369                      */
+    int32_t reserved;
+} ellc_lc_stats;
+
 typedef struct ellc_handle ellc_handle;
 
 /* ---- lifetime -------------------------------------------------------------------------------------------------- */
@@ -144,6 +159,14 @@ int ellc_upload_keyframe_hypotheses(ellc_handle* h, int32_t slot, const uint8_t*
 int ellc_read_keyframe_occupancy(ellc_handle* h, int32_t slot, int32_t* n_valid, float* occupancy);
 /* depth_pyramid[level] (0 = invalid) and depthvararrptr[level] (-1 = invalid) as resident on the device. */
 int ellc_read_keyframe_depth(ellc_handle* h, int32_t slot, int32_t level, float* depth, float* var);
+
+/* Loop-closure candidate gating.  ellc_frame_histograms: calculateImageHistogram (src/GlobalOptimize.cpp:40-100)
+ * for n uploaded frame slots; the histograms stay resident (hist, n x 256 floats, may be NULL).  ellc_lc_gate: the statistics and
+ * the test findMatch applies to one (loop frame, test frame) candidate (:351-369), for n candidates at once; the id-gap test
+ * (MIN_MATCH_DIFFERENCE, :346) and the ring / window walk stay with the caller, who takes the first passing candidate. */
+int ellc_frame_histograms(ellc_handle* h, int32_t n, const int32_t* frame_slots, float* hist);
+int ellc_lc_gate(ellc_handle* h, int32_t n, const ellc_lc_candidate* candidates, float match_threshold, float max_rel_view_angle,
+                 ellc_lc_stats* stats);
 
 int ellc_frame_image_devptr(ellc_handle* h, int32_t frame_slot, uint8_t** image);
 int ellc_keyframe_devptrs(ellc_handle* h, int32_t kf_slot, uint8_t** image, float** depth, float** var,

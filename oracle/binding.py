@@ -167,6 +167,25 @@ def update_depth_image(valid, inv_depth_smoothed, variance_smoothed):
     return dict(valid_out=valid, depth=d, var=v, n_valid=n, occupancy=occ.value)
 
 
+def image_histogram(img):
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.empty(256, np.float32)
+    lib().ellc_oracle_image_histogram(_p(img), img.size, _p(out))
+    return out
+
+
+def hist_kl_div(h1, h2):
+    _l = lib()
+    _l.ellc_oracle_hist_kl_div.restype = C.c_double
+    return _l.ellc_oracle_hist_kl_div(_p(np.ascontiguousarray(h1, np.float32)), _p(np.ascontiguousarray(h2, np.float32)))
+
+
+def rotation_stats(pose1, pose2):
+    rms, ang = C.c_float(), C.c_float()
+    lib().ellc_oracle_rotation_stats(_p(_f6(pose1)), _p(_f6(pose2)), C.byref(rms), C.byref(ang))
+    return rms.value, ang.value
+
+
 def se3_exp(pose):
     T = np.empty(16, np.float32)
     lib().ellc_oracle_se3_exp(_p(_f6(pose)), _p(T))

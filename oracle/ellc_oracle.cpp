@@ -758,6 +758,38 @@ int ellc_oracle_update_depth_image(int w, int h, uint8_t* valid, const float* id
     return (int)count;
 }
 
+void ellc_oracle_image_histogram(const uint8_t* img, int n_pixels, float hist[256]) {
+    for (int i = 0; i < 256; ++i) hist[i] = 0.f;
+    for (int i = 0; i < n_pixels; ++i) hist[img[i]] += 1.0f;          // cv::calcHist: integer counts stored as float
+    float sum = 0;
+    for (int i = 0; i < 256; ++i) sum += hist[i];                     // src/GlobalOptimize.cpp:78-83
+    for (int i = 0; i < 256; ++i) hist[i] /= sum;                     // :85-88
+}
+
+double ellc_oracle_hist_kl_div(const float h1[256], const float h2[256]) {
+    double result = 0;
+    for (int j = 0; j < 256; ++j) {
+        double p = h1[j], q = h2[j];
+        if (std::fabs(p) <= DBL_EPSILON) continue;
+        if (std::fabs(q) <= DBL_EPSILON) q = 1e-10;
+        result += p * std::log(p / q);
+    }
+    return result;
+}
+
+void ellc_oracle_rotation_stats(const float p1[6], const float p2[6], float* rms_error, float* relative_view_angle) {
+    // src/GlobalOptimize.cpp:424-437; pow(float, int/double) promotes to double, the assignment rounds to float
+    *rms_error = (float)std::pow(std::pow((double)(p1[0] - p2[0]), 2) + std::pow((double)(p1[1] - p2[1]), 2) + std::pow((double)(p1[2] - p2[2]), 2), 0.5);
+    float v1[3], v2[3];
+    M4 T1 = mat_exp_f32(se3_hat(p1)), T2 = mat_exp_f32(se3_hat(p2));   // calculateViewVec :439-452: third row of R
+    for (int i = 0; i < 3; ++i) { v1[i] = T1.a[8 + i]; v2[i] = T2.a[8 + i]; }
+    const float mag1 = (float)std::pow((double)(v1[0] * v1[0] + v1[1] * v1[1] + v1[2] * v1[2]), 0.5);
+    const float mag2 = (float)std::pow((double)(v2[0] * v2[0] + v2[1] * v2[1] + v2[2] * v2[2]), 0.5);
+    float a = std::acos((v1[0] * v2[0] + v1[1] * v2[1] + v1[2] * v2[2]) / (mag1 * mag2));
+    a = (a * 180) / 3.14f;
+    *relative_view_angle = a;
+}
+
 void ellc_oracle_se3_exp(const float pose[6], float T[16]) {
     M4 r = mat_exp_f32(se3_hat(pose));
     std::memcpy(T, r.a, sizeof(r.a));

@@ -81,5 +81,38 @@ def main():
     print("wrote", os.listdir(HERE))
 
 
+def main_gating():
+    """Loop-closure gating (src/GlobalOptimize.cpp:40-122, :424-452): cv2.calcHist / cv2.compareHist(KL_DIV) vectors and
+    float64 view angles; written to their own file so that the older fixtures stay byte-identical."""
+    import cv2
+    import scipy.linalg as sl
+    rng = np.random.default_rng(20261018)
+    base = rng.integers(0, 256, (60, 80), dtype=np.uint8)
+    imgs = [base, np.clip(base.astype(int) + rng.integers(-25, 26, base.shape), 0, 255).astype(np.uint8),
+            (base // 2).astype(np.uint8), np.full((60, 80), 77, np.uint8), rng.integers(100, 140, (60, 80), dtype=np.uint8)]
+    hists = []
+    for im in imgs:
+        hst = cv2.calcHist([im], [0], None, [256], [0, 256]).ravel().astype(np.float32)
+        s_ = np.float32(0)
+        for v in hst:
+            s_ = np.float32(s_ + v)
+        hists.append((hst / s_).astype(np.float32))
+    kl = np.array([[cv2.compareHist(a.reshape(-1, 1), b.reshape(-1, 1), cv2.HISTCMP_KL_DIV) for b in hists] for a in hists], np.float64)
+    poses = (rng.standard_normal((8, 6)) * np.array([0.08, 0.08, 0.08, 0.3, 0.3, 0.3])).astype(np.float32)
+    ang = np.zeros((8, 8)); rms = np.zeros((8, 8))
+    for i in range(8):
+        for j in range(8):
+            v1 = sl.expm(hat(poses[i].astype(np.float64)))[2, :3]; v2 = sl.expm(hat(poses[j].astype(np.float64)))[2, :3]
+            ang[i, j] = np.degrees(np.arccos(np.clip(v1 @ v2 / (np.linalg.norm(v1) * np.linalg.norm(v2)), -1, 1))) * (np.pi / 3.14)
+            rms[i, j] = np.linalg.norm(poses[i, :3].astype(np.float64) - poses[j, :3].astype(np.float64))
+    np.savez_compressed(os.path.join(HERE, "gating_vectors.npz"), images=np.stack(imgs), hists=np.stack(hists), kl=kl, poses=poses,
+                        view_angle_deg=ang, rms=rms)
+    print("wrote gating_vectors.npz")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "gating":
+        main_gating()
+    else:
+        main()
+        main_gating()
