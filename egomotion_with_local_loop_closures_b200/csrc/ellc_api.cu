@@ -478,7 +478,12 @@ static int track_launch(ellc_handle* h, int n, const ellc_pair* pairs, bool want
     if (const char* e = std::getenv("ELLC_DEBUG_NO_UPDATE")) if (*e == '1') p.no_update = 1;
     if (const char* e = std::getenv("ELLC_DEBUG_MAX_ITER")) std::sscanf(e, "%d,%d,%d,%d", &p.max_iter[0], &p.max_iter[1], &p.max_iter[2], &p.max_iter[3]);
     if (const char* e = std::getenv("ELLC_DEBUG_NO_STOP")) if (*e == '1') p.stop_threshold = -1.0f;
-    int l = launch_track(h->stream, p, cluster, h->cfg.arithmetic == ELLC_ARITH_STRICT);
+    // Scheduling of the forward pairs: a cluster of CTAs per pair (few pairs), one CTA per 1..4 lockstep pairs, or (diagnostic,
+    // ELLC_SCHED=ws) the warp-specialised kernel whose solver warp overlaps K5 with the other pair's K4.
+    bool ws = false;                                       // measured slower than one CTA per pair on the B200 (see gn_track_ws_kernel)
+    if (const char* e = std::getenv("ELLC_SCHED")) ws = (cluster == 1) && (std::string(e) == "ws");
+    int l = ws ? launch_track_ws(h->stream, p, h->cfg.arithmetic == ELLC_ARITH_STRICT)
+               : launch_track(h->stream, p, cluster, h->cfg.arithmetic == ELLC_ARITH_STRICT);
     if (l < 0) { h->err = std::string("track kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()); return ELLC_ERR_CUDA; }
     h->launches += l;
     if (n_fwd < n) {

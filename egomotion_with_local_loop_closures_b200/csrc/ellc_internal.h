@@ -38,6 +38,8 @@ int launch_pull_host(cudaStream_t st, void* dst, const void* src_host_devptr, si
 // Launches the GN tracking kernel for p.n_pairs pairs with `cluster` CTAs per pair.  Returns kernels launched (1) or a
 // negative value on launch-configuration failure (cudaGetLastError carries the reason).
 int launch_track(cudaStream_t st, const TrackParams& p, int cluster, bool strict);
+// warp-specialised forward kernel (8 pixel warps + 1 solver warp, two pairs per CTA in a ping-pong pipeline); large batches
+int launch_track_ws(cudaStream_t st, const TrackParams& p, bool strict);
 // loop-closure (inverse-compositional constant-weight) variant: one CTA per pair, pairs = p.order[0 .. p.n_pairs)
 int launch_track_lc(cudaStream_t st, const TrackParams& p, bool strict);
 // single-thread kernel running solve_update_f on the device (ellc_solve_update)
