@@ -114,13 +114,28 @@ def setup_bytes(n_frames, n_kf):
 # clocks
 # ----------------------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region: NVML in a thread (5 ms period, no start-up latency);
+    falls back to `nvidia-smi -lms 50` when pynvml is unavailable.  mark() brackets the timed region; samples outside are dropped."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.rows, self.proc, self.idx = [], None, gpu_index
+        self.idx, self.rows, self.proc, self.stop_flag, self.t0, self.t1, self.nvml = gpu_index, [], None, False, None, None, None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.idx]) if vis and vis.split(",")[self.idx].isdigit() else self.idx
+            self.nvml = (pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys))
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.nvml[1], pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -129,11 +144,40 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv, hd = self.nvml
+        while not self.stop_flag:
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(hd, nv.NVML_CLOCK_SM))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(hd))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(hd))
+                self.rows.append((time.perf_counter(), mhz, mask))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
+        self.stop_flag = True
+        inside = lambda t: (self.t0 is None or t >= self.t0) and (self.t1 is None or t <= self.t1)
+        if self.nvml:
+            self.thread.join(timeout=1)
+            rows = [r for r in self.rows if inside(r[0])] or self.rows[-3:]
+            reasons = sorted({name for _, _, m in rows for bit, name in self.REASONS.items() if m & bit})
+            sm = [r[1] for r in rows]
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "samples": len(sm), "reasons": reasons,
+                    "source": "nvml, 5 ms period, timed region only"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -143,7 +187,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for _, r in self.rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 8:
                 continue
@@ -155,7 +199,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi -lms 50 (warm-up + timed region)"}
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -372,6 +416,8 @@ def main():
         kernel_ms.clear()
         trk.reset_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if clk:
+            clk.mark_begin()
         e0.record(stream)
         for _ in range(steps):
             res = fn()
@@ -379,6 +425,8 @@ def main():
             res = drain()
         e1.record(stream)
         barrier()
+        if clk:
+            clk.mark_end()
         ms = e0.elapsed_time(e1)
         launches = trk.launch_count()
         clocks = clk.stop() if clk else None
