@@ -263,7 +263,9 @@ def main():
 
     # ---- data first (fork-based rendering must precede CUDA initialisation)
     t_setup = time.time()
-    wl = build_workload(args.keyframes, args.frames, args.pairs_per_frame, seed=rank)
+    # every rank renders its own segment: share the host cores between the ranks of the node
+    wl = build_workload(args.keyframes, args.frames, args.pairs_per_frame, seed=rank,
+                        workers=max(1, min(32, (os.cpu_count() or 1) // max(1, world))))
     n_pairs = len(wl["kf_idx"])
 
     import torch
