@@ -72,11 +72,12 @@ def shard_pairs(kf_ids, frame_ids, world_size):
     return [np.nonzero(rank_of == r)[0] for r in range(world_size)]
 
 
-def gather_results(local_records, local_indices, n_total, group=None, device=None):
+def gather_results(local_records, local_indices, n_total, group=None, device=None, counts=None):
     """All-gather variable-length shards of fixed-size records and restore the global pair order.
 
     local_records: (n_local, record_bytes) uint8 torch tensor (CUDA for NCCL, CPU for gloo) or numpy structured array.
-    local_indices: global pair indices of the local records.  Returns a (n_total, record_bytes) uint8 tensor on every rank.
+    local_indices: global pair indices of the local records.  counts: optional per-rank record counts (skips their exchange and
+    its host synchronisation).  Returns a (n_total, record_bytes) uint8 tensor on every rank.
     """
     import torch
     import torch.distributed as dist
@@ -93,10 +94,12 @@ def gather_results(local_records, local_indices, n_total, group=None, device=Non
     if world == 1:
         out[idx] = local_records
         return out
-    n_local = torch.tensor([local_records.shape[0]], dtype=torch.int64, device=dev)
-    counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-    dist.all_gather(counts, n_local, group=group)
-    cmax = int(max(int(c.item()) for c in counts))
+    if counts is None:                                    # shard sizes: exchanged unless the caller already knows them (fixed sharding)
+        n_local = torch.tensor([local_records.shape[0]], dtype=torch.int64, device=dev)
+        counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(counts, n_local, group=group)
+        counts = [int(c.item()) for c in counts]
+    cmax = int(max(counts))
     pad_rec = torch.zeros((cmax, rec_bytes), dtype=torch.uint8, device=dev)
     pad_idx = torch.full((cmax,), -1, dtype=torch.int64, device=dev)
     pad_rec[: local_records.shape[0]] = local_records
