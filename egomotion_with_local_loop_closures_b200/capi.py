@@ -66,7 +66,7 @@ SYMBOLS = ["ellc_default_config", "ellc_create", "ellc_destroy", "ellc_last_erro
            "ellc_upload_frame", "ellc_upload_keyframe", "ellc_frame_image_devptr", "ellc_keyframe_devptrs",
            "ellc_prepare_frames", "ellc_prepare_keyframes", "ellc_track_batch", "ellc_track_batch_async",
            "ellc_results_download",
-           "ellc_synchronize", "ellc_gn_evaluate", "ellc_solve_update", "ellc_read_frame_level",
+           "ellc_synchronize", "ellc_gn_evaluate", "ellc_solve_update", "ellc_solve_update_rt", "ellc_read_frame_level",
            "ellc_read_keyframe_level", "ellc_level_dims", "ellc_concat_relative", "ellc_concat_origin",
            "ellc_se3_exp", "ellc_launch_count", "ellc_reset_launch_count", "ellc_stream", "ellc_stream_of", "ellc_selftest_division", "ellc_reset_keyframe_weights", "ellc_accumulate_weights",
            "ellc_finalise_weights", "ellc_upload_keyframe_weights", "ellc_read_keyframe_weights", "ellc_read_frame_weights",
@@ -101,6 +101,7 @@ def lib():
         L.ellc_results_download.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         L.ellc_gn_evaluate.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ellc_solve_update.argtypes = [C.c_void_p] + [C.c_void_p] * 5 + [C.POINTER(C.c_float)]
+        L.ellc_solve_update_rt.argtypes = [C.c_void_p] + [C.c_void_p] * 5 + [C.POINTER(C.c_float), C.c_void_p]
         L.ellc_read_frame_level.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ellc_read_keyframe_level.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
         L.ellc_level_dims.argtypes = [C.c_void_p, C.c_int32] + [C.POINTER(C.c_int32)] * 4
@@ -286,6 +287,14 @@ class Tracker:
         po = np.empty(6, np.float32); de = np.empty(6, np.float32); wp = C.c_float()
         self._chk(lib().ellc_solve_update(self._h, _p(H), _p(b), _p(pose), _p(po), _p(de), C.byref(wp)))
         return po, de, wp.value
+
+    def solve_update_rt(self, H, b, pose):
+        """solve_update + rows 0..2 of exp(hat(new pose)) exactly as K5 hands them to the next iteration."""
+        H = np.ascontiguousarray(np.asarray(H, np.float32).reshape(36))
+        b = np.ascontiguousarray(b, np.float32); pose = np.ascontiguousarray(pose, np.float32)
+        po = np.empty(6, np.float32); de = np.empty(6, np.float32); wp = C.c_float(); rt = np.empty(12, np.float32)
+        self._chk(lib().ellc_solve_update_rt(self._h, _p(H), _p(b), _p(pose), _p(po), _p(de), C.byref(wp), _p(rt)))
+        return po, de, wp.value, rt
 
     # -- read-back
     def level_dims(self, level):

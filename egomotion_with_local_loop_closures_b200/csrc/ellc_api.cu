@@ -788,12 +788,12 @@ int ellc_gn_evaluate(ellc_handle* h, int32_t kf_slot, int32_t frame_slot, int32_
     return ELLC_OK;
 }
 
-int ellc_solve_update(ellc_handle* h, const float H[36], const float b[6], const float pose_in[6], float pose_out[6],
-                      float delta[6], float* weighted_pose) {
+int ellc_solve_update_rt(ellc_handle* h, const float H[36], const float b[6], const float pose_in[6], float pose_out[6],
+                         float delta[6], float* weighted_pose, float rt_out[12]) {
     if (!h) return ELLC_ERR_INVALID;
     if (!H || !b || !pose_in || !pose_out || !delta || !weighted_pose) { h->err = "null argument"; return ELLC_ERR_INVALID; }
     CU_TRY(h, cudaSetDevice(h->cfg.device));
-    float in[54], outv[14];
+    float in[54], outv[26];
     for (int i = 0; i < 36; ++i) in[i] = H[i];
     for (int i = 0; i < 6; ++i) { in[36 + i] = b[i]; in[42 + i] = pose_in[i]; in[48 + i] = h->cfg.weight[i]; }
     int rc = stage_h2d(h, h->d_small, in, sizeof(in));
@@ -804,7 +804,13 @@ int ellc_solve_update(ellc_handle* h, const float H[36], const float b[6], const
     h->pin_used = 0;
     for (int i = 0; i < 6; ++i) { pose_out[i] = outv[i]; delta[i] = outv[6 + i]; }
     *weighted_pose = outv[12];
+    if (rt_out) for (int i = 0; i < 12; ++i) rt_out[i] = outv[14 + i];
     return ELLC_OK;
+}
+
+int ellc_solve_update(ellc_handle* h, const float H[36], const float b[6], const float pose_in[6], float pose_out[6],
+                      float delta[6], float* weighted_pose) {
+    return ellc_solve_update_rt(h, H, b, pose_in, pose_out, delta, weighted_pose, nullptr);
 }
 
 int ellc_level_dims(const ellc_handle* h, int32_t level, int32_t* pyr_w, int32_t* pyr_h, int32_t* cols, int32_t* rows) {

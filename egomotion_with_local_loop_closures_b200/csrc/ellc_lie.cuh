@@ -106,6 +106,7 @@ __host__ __device__ inline void m4_poly_f(float c2, const float (&P)[16], float 
 }
 // Solve A X = B for 4x4 fp32 with partial-pivot LU (the PartialPivLU::solve step of the Pade quotient, and .inverse()).
 __host__ __device__ inline void lu4_solve_f(const float (&Ain)[16], const float (&Bin)[16], float (&X)[16]) {
+    // (loops with constant bounds and the triangular condition inside: see invert6_lu_warp)
     constexpr int n = 4;
     float A[16], B[16];
     ELLC_UNROLL
@@ -115,30 +116,36 @@ __host__ __device__ inline void lu4_solve_f(const float (&Ain)[16], const float 
         int p = i;
         float best = fabsf(A[i * n + i]);
         ELLC_UNROLL
-        for (int r = i + 1; r < n; ++r) {
-            const float v = fabsf(A[r * n + i]);
-            if (v > best) { best = v; p = r; }
+        for (int r = 1; r < n; ++r) {
+            if (r > i) {
+                const float v = fabsf(A[r * n + i]);
+                if (v > best) { best = v; p = r; }
+            }
         }
         ELLC_UNROLL
-        for (int r = i + 1; r < n; ++r) {                 // swap rows i and p (p is data dependent: select, don't index)
-            const bool sw = (p == r);
-            ELLC_UNROLL
-            for (int c = 0; c < n; ++c) {
-                const float a0 = A[i * n + c], a1 = A[r * n + c];
-                A[i * n + c] = sw ? a1 : a0; A[r * n + c] = sw ? a0 : a1;
-                const float b0 = B[i * n + c], b1 = B[r * n + c];
-                B[i * n + c] = sw ? b1 : b0; B[r * n + c] = sw ? b0 : b1;
+        for (int r = 1; r < n; ++r) {                     // swap rows i and p (p is data dependent: select, don't index)
+            if (r > i) {
+                const bool sw = (p == r);
+                ELLC_UNROLL
+                for (int c = 0; c < n; ++c) {
+                    const float a0 = A[i * n + c], a1 = A[r * n + c];
+                    A[i * n + c] = sw ? a1 : a0; A[r * n + c] = sw ? a0 : a1;
+                    const float b0 = B[i * n + c], b1 = B[r * n + c];
+                    B[i * n + c] = sw ? b1 : b0; B[r * n + c] = sw ? b0 : b1;
+                }
             }
         }
         const float piv = A[i * n + i];
         ELLC_UNROLL
-        for (int r = i + 1; r < n; ++r) {
-            const float f = ELLC_DIV(A[r * n + i], piv);
-            A[r * n + i] = f;
-            ELLC_UNROLL
-            for (int c = i + 1; c < n; ++c) A[r * n + c] = ELLC_SUB(A[r * n + c], ELLC_MUL(f, A[i * n + c]));
-            ELLC_UNROLL
-            for (int c = 0; c < n; ++c) B[r * n + c] = ELLC_SUB(B[r * n + c], ELLC_MUL(f, B[i * n + c]));
+        for (int r = 1; r < n; ++r) {
+            if (r > i) {
+                const float f = ELLC_DIV(A[r * n + i], piv);
+                A[r * n + i] = f;
+                ELLC_UNROLL
+                for (int c = 1; c < n; ++c) if (c > i) A[r * n + c] = ELLC_SUB(A[r * n + c], ELLC_MUL(f, A[i * n + c]));
+                ELLC_UNROLL
+                for (int c = 0; c < n; ++c) B[r * n + c] = ELLC_SUB(B[r * n + c], ELLC_MUL(f, B[i * n + c]));
+            }
         }
     }
     ELLC_UNROLL
@@ -147,7 +154,7 @@ __host__ __device__ inline void lu4_solve_f(const float (&Ain)[16], const float 
         for (int i = n - 1; i >= 0; --i) {
             float s = B[i * n + c];
             ELLC_UNROLL
-            for (int k = i + 1; k < n; ++k) s = ELLC_SUB(s, ELLC_MUL(A[i * n + k], X[k * n + c]));
+            for (int k = 1; k < n; ++k) if (k > i) s = ELLC_SUB(s, ELLC_MUL(A[i * n + k], X[k * n + c]));
             X[i * n + c] = ELLC_DIV(s, A[i * n + i]);
         }
     }
@@ -267,33 +274,41 @@ __host__ __device__ inline bool invert6_lu_f(const float (&Hin)[36], float (&Hin
         int k = i;
         float best = fabsf(A[i * m + i]);
         ELLC_UNROLL
-        for (int j = i + 1; j < m; ++j) {
-            const float v = fabsf(A[j * m + i]);
-            if (v > best) { best = v; k = j; }
+        for (int j = 1; j < m; ++j) {
+            if (j > i) {
+                const float v = fabsf(A[j * m + i]);
+                if (v > best) { best = v; k = j; }
+            }
         }
         if (best < eps) ok = false;                           // LUImpl returns 0 here; keep going branch-free, zero below
         ELLC_UNROLL
-        for (int j = i + 1; j < m; ++j) {                     // swap rows i and k: columns i.. of A, all of B
-            const bool sw = (k == j);
-            ELLC_UNROLL
-            for (int c = i; c < m; ++c) {
-                const float a0 = A[i * m + c], a1 = A[j * m + c];
-                A[i * m + c] = sw ? a1 : a0; A[j * m + c] = sw ? a0 : a1;
-            }
-            ELLC_UNROLL
-            for (int c = 0; c < m; ++c) {
-                const float b0 = B[i * m + c], b1 = B[j * m + c];
-                B[i * m + c] = sw ? b1 : b0; B[j * m + c] = sw ? b0 : b1;
+        for (int j = 1; j < m; ++j) {                         // swap rows i and k: columns i.. of A, all of B
+            if (j > i) {
+                const bool sw = (k == j);
+                ELLC_UNROLL
+                for (int c = 0; c < m; ++c) {
+                    if (c >= i) {
+                        const float a0 = A[i * m + c], a1 = A[j * m + c];
+                        A[i * m + c] = sw ? a1 : a0; A[j * m + c] = sw ? a0 : a1;
+                    }
+                }
+                ELLC_UNROLL
+                for (int c = 0; c < m; ++c) {
+                    const float b0 = B[i * m + c], b1 = B[j * m + c];
+                    B[i * m + c] = sw ? b1 : b0; B[j * m + c] = sw ? b0 : b1;
+                }
             }
         }
         const float d = ELLC_DIV(-1.f, A[i * m + i]);
         ELLC_UNROLL
-        for (int j = i + 1; j < m; ++j) {
-            const float alpha = ELLC_MUL(A[j * m + i], d);
-            ELLC_UNROLL
-            for (int c = i + 1; c < m; ++c) A[j * m + c] = ELLC_ADD(A[j * m + c], ELLC_MUL(alpha, A[i * m + c]));
-            ELLC_UNROLL
-            for (int c = 0; c < m; ++c) B[j * m + c] = ELLC_ADD(B[j * m + c], ELLC_MUL(alpha, B[i * m + c]));
+        for (int j = 1; j < m; ++j) {
+            if (j > i) {
+                const float alpha = ELLC_MUL(A[j * m + i], d);
+                ELLC_UNROLL
+                for (int c = 1; c < m; ++c) if (c > i) A[j * m + c] = ELLC_ADD(A[j * m + c], ELLC_MUL(alpha, A[i * m + c]));
+                ELLC_UNROLL
+                for (int c = 0; c < m; ++c) B[j * m + c] = ELLC_ADD(B[j * m + c], ELLC_MUL(alpha, B[i * m + c]));
+            }
         }
         A[i * m + i] = -d;
     }
@@ -303,7 +318,7 @@ __host__ __device__ inline bool invert6_lu_f(const float (&Hin)[36], float (&Hin
         for (int j = 0; j < m; ++j) {
             float s = B[i * m + j];
             ELLC_UNROLL
-            for (int c = i + 1; c < m; ++c) s = ELLC_SUB(s, ELLC_MUL(A[i * m + c], B[c * m + j]));
+            for (int c = 1; c < m; ++c) if (c > i) s = ELLC_SUB(s, ELLC_MUL(A[i * m + c], B[c * m + j]));
             B[i * m + j] = ELLC_MUL(s, A[i * m + i]);
         }
     }
@@ -343,6 +358,8 @@ __host__ __device__ inline bool solve_update_f(const float (&H)[36], const float
 // The same LU as invert6_lu_f, with the six right-hand-side columns of [A | I] spread over lanes (lane % 6 owns one column
 // of the inverse) while every lane eliminates A redundantly: identical pivots, identical operations per entry, 1/4 of the
 // serial instruction count.  Returns column (lane % 6) of the inverse in col[0..5]; *ok as invert6_lu_f.
+// All loops have constant bounds with the triangular condition inside: written as `for (j = i + 1; ...)` nvcc leaves the row
+// loops rolled after unrolling the outer one, and A then lives in local memory with dynamic addressing (LDL/STL chains).
 __device__ inline void invert6_lu_warp(const float (&Hin)[36], int lane, float (&col)[6], bool* okp) {
     constexpr int m = 6;
     const int mycol = lane % 6;
@@ -358,29 +375,39 @@ __device__ inline void invert6_lu_warp(const float (&Hin)[36], int lane, float (
         int k = i;
         float best = fabsf(A[i * m + i]);
         ELLC_UNROLL
-        for (int j = i + 1; j < m; ++j) {
-            const float v = fabsf(A[j * m + i]);
-            if (v > best) { best = v; k = j; }
+        for (int j = 1; j < m; ++j) {
+            if (j > i) {
+                const float v = fabsf(A[j * m + i]);
+                if (v > best) { best = v; k = j; }
+            }
         }
         if (best < eps) ok = false;
-        ELLC_UNROLL
-        for (int j = i + 1; j < m; ++j) {
-            const bool sw = (k == j);
+        if (k != i) {                                          // warp-uniform (A is replicated); usually the diagonal is the pivot
             ELLC_UNROLL
-            for (int c = i; c < m; ++c) {
-                const float a0 = A[i * m + c], a1 = A[j * m + c];
-                A[i * m + c] = sw ? a1 : a0; A[j * m + c] = sw ? a0 : a1;
+            for (int j = 1; j < m; ++j) {
+                if (j > i) {
+                    const bool sw = (k == j);
+                    ELLC_UNROLL
+                    for (int c = 0; c < m; ++c) {
+                        if (c >= i) {
+                            const float a0 = A[i * m + c], a1 = A[j * m + c];
+                            A[i * m + c] = sw ? a1 : a0; A[j * m + c] = sw ? a0 : a1;
+                        }
+                    }
+                    const float b0 = B[i], b1 = B[j];
+                    B[i] = sw ? b1 : b0; B[j] = sw ? b0 : b1;
+                }
             }
-            const float b0 = B[i], b1 = B[j];
-            B[i] = sw ? b1 : b0; B[j] = sw ? b0 : b1;
         }
         const float d = ELLC_DIV(-1.f, A[i * m + i]);
         ELLC_UNROLL
-        for (int j = i + 1; j < m; ++j) {
-            const float alpha = ELLC_MUL(A[j * m + i], d);
-            ELLC_UNROLL
-            for (int c = i + 1; c < m; ++c) A[j * m + c] = ELLC_ADD(A[j * m + c], ELLC_MUL(alpha, A[i * m + c]));
-            B[j] = ELLC_ADD(B[j], ELLC_MUL(alpha, B[i]));
+        for (int j = 1; j < m; ++j) {
+            if (j > i) {
+                const float alpha = ELLC_MUL(A[j * m + i], d);
+                ELLC_UNROLL
+                for (int c = 1; c < m; ++c) if (c > i) A[j * m + c] = ELLC_ADD(A[j * m + c], ELLC_MUL(alpha, A[i * m + c]));
+                B[j] = ELLC_ADD(B[j], ELLC_MUL(alpha, B[i]));
+            }
         }
         A[i * m + i] = -d;
     }
@@ -388,7 +415,7 @@ __device__ inline void invert6_lu_warp(const float (&Hin)[36], int lane, float (
     for (int i = m - 1; i >= 0; --i) {
         float s = B[i];
         ELLC_UNROLL
-        for (int c = i + 1; c < m; ++c) s = ELLC_SUB(s, ELLC_MUL(A[i * m + c], B[c]));
+        for (int c = 1; c < m; ++c) if (c > i) s = ELLC_SUB(s, ELLC_MUL(A[i * m + c], B[c]));
         B[i] = ELLC_MUL(s, A[i * m + i]);
     }
     ELLC_UNROLL
@@ -396,12 +423,112 @@ __device__ inline void invert6_lu_warp(const float (&Hin)[36], int lane, float (
     *okp = ok;
 }
 
-// solve_update_f executed by one full warp (all 32 lanes call it with the same arguments and get the same results).
-// Rt_pose is exp(hat(pose)) as computed for the current iteration (its 4th row is exactly [0 0 0 1]), so only exp(delta)
-// has to be evaluated for the composition.
-__device__ inline bool solve_update_warp(const float (&H)[36], const float (&b)[6], const float (&weight)[6],
-                                         const float (&Rt_pose)[12], float (&pose)[6], float (&delta)[6],
-                                         float* weighted_pose, int lane) {
+// ---- 4x4 fp32 algebra spread over the lanes of a warp ----------------------------------------------------------------
+// Lane l holds entry e = l & 15 (row e >> 2, column e & 3) of every matrix; lanes 16..31 mirror lanes 0..15.  Each entry is
+// produced by exactly the operation sequence of the serial helpers above (m4_mul_f, m4_poly_f, lu4_solve_f, se3_exp_pade_f),
+// so the results are bit-identical to them; only who computes which entry changes.  A 4x4 product costs 8 shuffles + 7
+// arithmetic instructions per lane instead of 112 on one thread, the Pade quotient 7 divisions instead of 22.
+constexpr unsigned kFullWarp = 0xffffffffu;
+__device__ __forceinline__ float m4w_mul(float x, float y, int e) {
+    const int r4 = e & 12, c = e & 3;
+    float s = ELLC_MUL(__shfl_sync(kFullWarp, x, r4), __shfl_sync(kFullWarp, y, c));
+    ELLC_UNROLL
+    for (int k = 1; k < 4; ++k) s = ELLC_ADD(s, ELLC_MUL(__shfl_sync(kFullWarp, x, r4 + k), __shfl_sync(kFullWarp, y, 4 * k + c)));
+    return s;
+}
+// lu4_solve_f: entry e of X with A X = B
+__device__ __forceinline__ float lu4w_solve(float A, float B, int e) {
+    const int r = e >> 2, c = e & 3;
+    ELLC_UNROLL
+    for (int i = 0; i < 3; ++i) {                              // step i = 3 of the serial loop has nothing left to do
+        int p = i;
+        float best = fabsf(__shfl_sync(kFullWarp, A, 4 * i + i));
+        ELLC_UNROLL
+        for (int j = i + 1; j < 4; ++j) {
+            const float v = fabsf(__shfl_sync(kFullWarp, A, 4 * j + i));
+            if (v > best) { best = v; p = j; }
+        }
+        if (p != i) {                                          // warp-uniform: every lane saw the same column
+            const int sr = (r == i) ? p : (r == p) ? i : r;
+            A = __shfl_sync(kFullWarp, A, 4 * sr + c);
+            B = __shfl_sync(kFullWarp, B, 4 * sr + c);
+        }
+        const float piv = __shfl_sync(kFullWarp, A, 5 * i);
+        const float ari = __shfl_sync(kFullWarp, A, 4 * r + i);
+        const float ai = __shfl_sync(kFullWarp, A, 4 * i + c);
+        const float bi = __shfl_sync(kFullWarp, B, 4 * i + c);
+        if (r > i) {
+            const float f = ELLC_DIV(ari, piv);
+            if (c > i) A = ELLC_SUB(A, ELLC_MUL(f, ai));
+            else if (c == i) A = f;
+            B = ELLC_SUB(B, ELLC_MUL(f, bi));
+        }
+    }
+    const float d = __shfl_sync(kFullWarp, A, 5 * r);
+    const float a1 = __shfl_sync(kFullWarp, A, 4 * r + 1), a2 = __shfl_sync(kFullWarp, A, 4 * r + 2),
+                a3 = __shfl_sync(kFullWarp, A, 4 * r + 3);
+    float X = ELLC_DIV(B, d);                                  // final for row 3
+    const float x3 = __shfl_sync(kFullWarp, X, 12 + c);
+    if (r == 2) X = ELLC_DIV(ELLC_SUB(B, ELLC_MUL(a3, x3)), d);
+    const float x2 = __shfl_sync(kFullWarp, X, 8 + c);
+    if (r == 1) X = ELLC_DIV(ELLC_SUB(ELLC_SUB(B, ELLC_MUL(a2, x2)), ELLC_MUL(a3, x3)), d);
+    const float x1 = __shfl_sync(kFullWarp, X, 4 + c);
+    if (r == 0) X = ELLC_DIV(ELLC_SUB(ELLC_SUB(ELLC_SUB(B, ELLC_MUL(a1, x1)), ELLC_MUL(a2, x2)), ELLC_MUL(a3, x3)), d);
+    return X;
+}
+// se3_exp_pade_f: entry e of exp(hat(p)); p is the same in every lane.  Not inlined: K5 calls it twice per iteration and the
+// solver's code should stay small (it runs on one warp per CTA and misses in the instruction cache otherwise).
+static __device__ __noinline__ float se3_exp_pade_warp(float p0, float p1, float p2, float p3, float p4, float p5, int e) {
+    const float p[6] = {p0, p1, p2, p3, p4, p5};          // by value: an array reference would put the caller's pose in local memory
+    float M = 0.f;
+    M = (e == 1) ? -p[2] : M; M = (e == 2) ? p[1] : M;  M = (e == 3) ? p[3] : M;
+    M = (e == 4) ? p[2] : M;  M = (e == 6) ? -p[0] : M; M = (e == 7) ? p[4] : M;
+    M = (e == 8) ? -p[1] : M; M = (e == 9) ? p[0] : M;  M = (e == 11) ? p[5] : M;
+    // L1 norm: column sums in the serial order (the zero entries add exactly nothing)
+    const float a0 = fabsf(p[0]), a1 = fabsf(p[1]), a2 = fabsf(p[2]);
+    float l1 = fmaxf(0.f, ELLC_ADD(a2, a1));
+    l1 = fmaxf(l1, ELLC_ADD(a2, a0));
+    l1 = fmaxf(l1, ELLC_ADD(a1, a0));
+    l1 = fmaxf(l1, ELLC_ADD(ELLC_ADD(fabsf(p[3]), fabsf(p[4])), fabsf(p[5])));
+    const bool diag = (e % 5) == 0;
+    float U, V;
+    int squarings = 0;
+    if (l1 < 4.258730016922831e-001f) {
+        const float A2 = m4w_mul(M, M, e);
+        const float tmp = ELLC_ADD(ELLC_MUL(1.f, A2), diag ? 60.f : 0.f);
+        U = m4w_mul(M, tmp, e);
+        V = ELLC_ADD(ELLC_MUL(12.f, A2), diag ? 120.f : 0.f);
+    } else if (l1 < 1.880152677804762e+000f) {
+        const float A2 = m4w_mul(M, M, e);
+        const float A4 = m4w_mul(A2, A2, e);
+        const float tmp = ELLC_ADD(ELLC_ADD(ELLC_MUL(1.f, A4), ELLC_MUL(420.f, A2)), diag ? 15120.f : 0.f);
+        U = m4w_mul(M, tmp, e);
+        V = ELLC_ADD(ELLC_ADD(ELLC_MUL(30.f, A4), ELLC_MUL(3360.f, A2)), diag ? 30240.f : 0.f);
+    } else {
+        (void)frexpf(ELLC_DIV(l1, 3.925724783138660f), &squarings);
+        if (squarings < 0) squarings = 0;
+        const float sc = ldexpf(1.0f, squarings);
+        const float A = ELLC_DIV(M, sc);
+        const float A2 = m4w_mul(A, A, e);
+        const float A4 = m4w_mul(A2, A2, e);
+        const float A6 = m4w_mul(A4, A2, e);
+        const float tmp = ELLC_ADD(ELLC_ADD(ELLC_ADD(ELLC_MUL(1.f, A6), ELLC_MUL(1512.f, A4)), ELLC_MUL(277200.f, A2)),
+                                   diag ? 8648640.f : 0.f);
+        U = m4w_mul(A, tmp, e);
+        V = ELLC_ADD(ELLC_ADD(ELLC_ADD(ELLC_MUL(56.f, A6), ELLC_MUL(25200.f, A4)), ELLC_MUL(1995840.f, A2)),
+                     diag ? 17297280.f : 0.f);
+    }
+    float T = lu4w_solve(ELLC_ADD(-U, V), ELLC_ADD(U, V), e);
+    for (int s = 0; s < squarings; ++s) T = m4w_mul(T, T, e);
+    return T;
+}
+
+// solve_update_f executed by one full warp (all 32 lanes call it with the same H, b, weight, pose and get the same pose, delta,
+// weighted_pose).  The 4x4 part runs lane-distributed: rt_pose_e is entry (lane & 15) of exp(hat(pose)) as computed for the
+// current iteration (rows 0..2 from Rt, row 3 exactly [0 0 0 1]), and *rt_new_e returns the same entry of exp(hat(new pose)) for
+// the next iteration (src/PixelWisePyramid.cpp:153-173), so only exp(delta) and exp(new pose) are evaluated.
+__device__ inline bool solve_update_warp(const float (&H)[36], const float (&b)[6], const float (&weight)[6], float rt_pose_e,
+                                         float (&pose)[6], float (&delta)[6], float* weighted_pose, float* rt_new_e, int lane) {
     float col[6];
     bool ok;
     invert6_lu_warp(H, lane, col, &ok);
@@ -412,20 +539,22 @@ __device__ inline bool solve_update_warp(const float (&H)[36], const float (&b)[
         const double term = __dmul_rn((double)col[i], bk);
         double s = 0.0;
         ELLC_UNROLL
-        for (int k = 0; k < 6; ++k) s = __dadd_rn(s, __shfl_sync(0xffffffffu, term, k));
+        for (int k = 0; k < 6; ++k) s = __dadd_rn(s, __shfl_sync(kFullWarp, term, k));
         delta[i] = -(float)s;
     }
     float wp = fabsf(ELLC_MUL(delta[0], weight[0]));
     ELLC_UNROLL
     for (int i = 1; i < 6; ++i) wp = ELLC_ADD(wp, fabsf(ELLC_MUL(delta[i], weight[i])));
     *weighted_pose = wp;
-    float Ta[16], Tb[16], T[16];
-    se3_exp_pade_f(delta, Ta);
+    const int e = lane & 15;
+    const float Ta = se3_exp_pade_warp(delta[0], delta[1], delta[2], delta[3], delta[4], delta[5], e);
+    const float Te = m4w_mul(Ta, rt_pose_e, e);
+    float T[16];
     ELLC_UNROLL
-    for (int i = 0; i < 12; ++i) Tb[i] = Rt_pose[i];
-    Tb[12] = Tb[13] = Tb[14] = 0.f; Tb[15] = 1.f;
-    m4_mul_f(Ta, Tb, T);
+    for (int i = 0; i < 12; ++i) T[i] = __shfl_sync(kFullWarp, Te, i);
+    T[12] = T[13] = T[14] = 0.f; T[15] = 1.f;                  // not read by the logarithm
     m4_log_f(T, pose);
+    *rt_new_e = se3_exp_pade_warp(pose[0], pose[1], pose[2], pose[3], pose[4], pose[5], e);
     return ok;
 }
 #endif  // __CUDACC__

@@ -223,6 +223,10 @@ int ellc_gn_evaluate(ellc_handle* h, int32_t kf_slot, int32_t frame_slot, int32_
 /* hessian.inv() + updatePose() (src/PixelWisePyramid.cpp:451-491) executed by the device code path. */
 int ellc_solve_update(ellc_handle* h, const float H[36], const float b[6], const float pose_in[6],
                       float pose_out[6], float delta[6], float* weighted_pose);
+/* The same, also returning rows 0..2 of exp(hat(pose_out)) as K5 hands them to the next iteration (SE3_vec,
+ * src/PixelWisePyramid.cpp:153-173); equals ellc_se3_exp(pose_out) bit for bit. */
+int ellc_solve_update_rt(ellc_handle* h, const float H[36], const float b[6], const float pose_in[6],
+                         float pose_out[6], float delta[6], float* weighted_pose, float rt_out[12]);
 
 /* ---- read-back of intermediate products (parity tests) ------------------------------------------------------------ */
 /* image_pyramid[level] (pyrDown chain) and gradientx/gradienty after updationOnPyrChange(level) (src/Frame.cpp:316-327).
