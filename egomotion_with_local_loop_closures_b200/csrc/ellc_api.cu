@@ -155,7 +155,9 @@ int ellc_create(const ellc_config* cfg, ellc_handle** out) {
     *out = nullptr;
     if (cfg->width < 16 || cfg->height < 16 || cfg->width > 2047 || cfg->height > 2047 || cfg->max_keyframes < 1 ||
         cfg->max_frames < 1) { g_create_err = "unsupported size / slot count"; return ELLC_ERR_INVALID; }
-    if (cfg->jacobian_at_warped) { g_create_err = "jacobian_at_warped (Pyramid.cpp variant) is not built yet"; return ELLC_ERR_INVALID; }
+    if (cfg->jacobian_at_warped && cfg->arithmetic != ELLC_ARITH_STRICT) {
+        g_create_err = "jacobian_at_warped (Pyramid.cpp variant) is built in the ELLC_ARITH_STRICT flavour only"; return ELLC_ERR_INVALID;
+    }
     for (int l = 0; l < kLevels; ++l)
         if (cfg->max_iter[l] < 0) { g_create_err = "negative max_iter"; return ELLC_ERR_INVALID; }
     int ndev = 0;

@@ -61,7 +61,8 @@ typedef struct ellc_config {
     float   stop_threshold;           /* 1.0f, src/ImageFunc.cpp:251                                              */
     int32_t arithmetic;               /* ELLC_ARITH_*                                                             */
     int32_t jacobian_at_warped;       /* 0: PixelWisePyramid.cpp Jacobian (keyframe pixel/depth);
-                                         1: Pyramid.cpp:99-130 variant (warped pixel, transformed depth)          */
+                                         1: Pyramid.cpp:99-130 variant (warped pixel, transformed depth, weight of an
+                                            out-of-bounds pixel not zeroed :629-651); needs ELLC_ARITH_STRICT          */
     int32_t max_keyframes;            /* keyframe slots resident on the device                                    */
     int32_t max_frames;               /* frame slots resident on the device                                       */
     int32_t ctas_per_pair;            /* thread-block cluster size per pair: 1,2,4,8; 0 = choose from batch size  */
