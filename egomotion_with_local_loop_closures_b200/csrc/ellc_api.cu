@@ -443,9 +443,15 @@ static int track_launch(ellc_handle* h, int n, const ellc_pair* pairs, bool want
     {
         std::vector<int> order(n);
         for (int i = 0; i < n; ++i) order[i] = i;
+        int kf_group = 0;                                  // EXPERIMENT: keyframes per schedule group (0 = frame-major over all keyframes)
+        if (const char* e = std::getenv("ELLC_ORDER_KF_GROUP")) kf_group = std::atoi(e);
         std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
             const int la = (pairs[a].flags & ELLC_PAIR_CONST_WEIGHT) ? 1 : 0, lb = (pairs[b].flags & ELLC_PAIR_CONST_WEIGHT) ? 1 : 0;
             if (la != lb) return la < lb;
+            if (kf_group > 0) {
+                const int ga = pairs[a].kf_slot / kf_group, gb = pairs[b].kf_slot / kf_group;
+                if (ga != gb) return ga < gb;
+            }
             if (pairs[a].frame_slot != pairs[b].frame_slot) return pairs[a].frame_slot < pairs[b].frame_slot;
             return pairs[a].kf_slot < pairs[b].kf_slot;
         });
