@@ -86,9 +86,9 @@ def _bandpass_field(rng, shape, wavelength, rel_bw=0.35):
 class SynthScene:
     """Textured height-field Z = h(X, Y) in world coordinates, rendered by exact ray/surface intersection."""
 
-    def __init__(self, width, height, seed_tex=1234, edge_gain=12.0, wavelength_px=56.0):
+    def __init__(self, width, height, seed_tex=1234, edge_gain=12.0, wavelength_px=56.0, k=None):
         self.width, self.height = int(width), int(height)
-        k = intrinsics(width, height)
+        k = k or intrinsics(width, height)                 # k: intrinsics override (the reference's compiled-in camera)
         self.fx, self.fy, self.cx, self.cy = (float(k[n]) for n in ("fx", "fy", "cx", "cy"))
         rng = np.random.default_rng(seed_tex)
         # surface: tilted plane + 4 low-frequency bumps, Z in ~[1.0, 2.2] over the visible region

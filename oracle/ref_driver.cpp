@@ -1,0 +1,237 @@
+// ref_driver.cpp -- builds the reference's OWN tracking sources into oracle/_ref/libellc_ref.so (TEST INFRASTRUCTURE ONLY).
+//
+// The reference (IITD-COMPUTER-VISION-GROUP/Egomotion_with_Local_Loop_Closures) needs OpenCV 3.0, Eigen 3.2.5 and Boost 1.59,
+// none of which exist in this image, and it ships no tests or golden vectors.  To pin the oracle restatement on the
+// reference's own code anyway, this translation unit #includes the UNMODIFIED reference sources where they lie
+// (-I/root/reference/src; nothing is copied into this repository) and compiles them against the stand-in headers under
+// oracle/shim/ (a minimal cv::Mat / Eigen::Matrix / boost::thread_group; the third-party arithmetic in them is our
+// restatement of the published algorithms, pinned separately against cv2 / scipy).  What runs here is therefore the
+// reference's per-pixel code (src/PixelWisePyramid.cpp), its samplers (src/Frame.h), pyramid / gradient / mask / pose
+// bookkeeping (src/Frame.cpp), intrinsics (src/UserDefinedFunc.cpp) and its driver GetImagePoseEstimate (src/ImageFunc.cpp).
+// The reference hard-codes its image size and intrinsics (src/ExternVariable.h:39-59: 480x270, fx = 410.6, fy = 409.0);
+// ellc_ref_dims reports them and the tests run the oracle and the CUDA path at exactly that configuration.
+//
+// One translation unit on purpose: util::FLAG_DO_UNDISTORTION is a `static bool` defined in a header (one copy per
+// translation unit, src/ExternVariable.h:61); SURVEY 8d runs without lens distortion, and only code in the same unit as
+// Frame.cpp can switch that copy off.
+#include "Frame.cpp"
+#include "EigenInitialization.cpp"
+#include "UserDefinedFunc.cpp"
+#include "PixelWisePyramid.cpp"
+#include "Pyramid.cpp"
+#include "ImageFunc.cpp"
+
+// ---- definitions that live in src/main.cpp (:34-60), which is not part of the tracking path --------------------------------
+int util::MAX_ITER[] = {4, 7, 9, 12};
+bool util::FLAG_ALTERNATE_GN_RA = false;
+int util::FLAG_IS_BOOTSTRAP = false;
+int util::BATCH_START_ID = 0;
+int util::BATCH_SIZE = 0;
+int util::NUM_GN_PROPAGATION = 0;
+int util::NUM_RA_PROPAGATION = 0;
+bool util::GAUSS_NEWTON_FLAG_ON = false;
+bool util::ROTATION_AVERAGING_FLAG_ON = false;
+bool util::FLAG_DO_LOOP_CLOSURE = false;
+bool util::FLAG_REPLICATE_NEW_DEPTH = false;
+bool util::FLAG_INITIALIZE_NONZERO_POSE = false;
+bool util::FLAG_SAVE_MATS = false;
+bool util::FLAG_DO_PARALLEL_SHORT_LOOP_CLOSURE = false;
+bool util::FLAG_DO_CONST_WEIGHT_POSE_ESTIMATION = false;
+bool util::FLAG_DO_PARALLEL_CONST_WEIGHT_POSE_EST = false;
+bool util::FLAG_USE_LOOP_CLOSURE_TRIGGER = false;
+bool util::EXIT_CONDITION = false;
+
+// ---- src/DisplayFunc.cpp (highgui windows): not on the path, FLAG_DISPLAY_IMAGES is false ------------------------------------
+FILE* STATE_FILE = nullptr;
+void MY_ASSERT_FUNC(bool) {}
+void DEBUG_COND_FUNC(bool) {}
+void DisplayIterationRes(frame*, Mat, String, int, bool) {}
+void DisplayInitialRes(frame*, frame*, String, int, bool) {}
+void DisplayWarpedImg(Mat, frame*, String, int, bool) {}
+void DisplayWeights(frame*, Mat, String, int, bool) {}
+void DisplayOriginalImg(Mat, frame*, String, int, bool) {}
+void DisplayColouredDepth(Mat, Mat) {}
+void DisplayIterationResPixelWise(Mat, frame*, String, int, bool) {}
+void DisplayInitialResPixelWise(Mat, frame*, String, int, bool) {}
+void DisplayWarpedImgPxelWise(Mat, frame*, String, int, bool) {}
+void DisplayWeightsPixelWise(Mat, frame*, String, int, bool) {}
+void DisplayOriginalImgPixelWise(Mat, frame*, String, int, bool) {}
+
+namespace {
+
+const int W0 = util::ORIG_COLS, H0 = util::ORIG_ROWS;
+
+// frame::frame(VideoCapture) (src/Frame.cpp:34-119) resizes the camera image by RESIZE_FACTOR = 1/4 and converts BGR -> gray:
+// feed it the 4x pixel-replicated, 3-channel version of the wanted image, which both steps return exactly.
+frame* make_frame(const uint8_t* gray) {
+    const int F = (int)util::DIM_FACTOR;
+    Mat big(H0 * F, W0 * F, CV_8UC3);
+    for (int y = 0; y < H0 * F; ++y) {
+        uchar* row = big.ptr<uchar>(y);
+        for (int x = 0; x < W0 * F; ++x) {
+            const uchar v = gray[(y / F) * W0 + (x / F)];
+            row[3 * x] = row[3 * x + 1] = row[3 * x + 2] = v;
+        }
+    }
+    VideoCapture cap(&big);
+    return new frame(cap);
+}
+
+// depthMap is 10 MB of fixed arrays with a constructor in src/DepthPropagation.cpp (the depth module, out of scope).  The
+// tracker only reads depthvararrptr[level] (src/PixelWisePyramid.cpp:348), so an all-zero object with those pointers set is
+// everything it needs; no member function of depthMap is ever called.
+struct DepthHolder {
+    depthMap* dm;
+    std::vector<float> var[4];
+    DepthHolder() : dm((depthMap*)std::calloc(1, sizeof(depthMap))) {}
+    ~DepthHolder() { std::free(dm); }
+};
+
+void set_keyframe_depth(frame* kf, DepthHolder& dh, const float* const* depth, const float* const* var) {
+    for (int l = 0; l < 4; ++l) {
+        const int r = H0 >> l, c = W0 >> l;
+        kf->depth_pyramid[l] = Mat::zeros(r, c, CV_32FC1);
+        for (int y = 0; y < r; ++y) std::memcpy(kf->depth_pyramid[l].ptr<float>(y), depth[l] + (size_t)y * c, (size_t)c * sizeof(float));
+        dh.var[l].assign(var[l], var[l] + (size_t)r * c);
+        dh.dm->depthvararrptr[l] = dh.var[l].data();
+    }
+    kf->depth = kf->depth_pyramid[0];
+}
+
+void init_once() {
+    util::FLAG_DO_UNDISTORTION = false;       // no lens distortion in the synthetic configurations
+}
+
+}  // namespace
+
+extern "C" {
+
+struct ellc_ref_iter {
+    float H[36];
+    float b[6];
+    float weighted_pose;
+    float pose_after[6];
+    float pad_;
+};
+struct ellc_ref_trace {
+    int n_selected[4];
+    int n_iters[4];
+    ellc_ref_iter it[4][12];
+    float final_pose[6];
+};
+
+// the reference's compile-time configuration (src/ExternVariable.h:39-62, :76, :148-149)
+void ellc_ref_dims(int* w, int* h, float* fx, float* fy, float* cx, float* cy) {
+    *w = W0; *h = H0; *fx = util::ORIG_FX; *fy = util::ORIG_FY; *cx = util::ORIG_CX; *cy = util::ORIG_CY;
+}
+
+// frame construction + updationOnPyrChange(level): image_pyramid[level] (pyrDown dims), gradientx / gradienty, and -- when a
+// depth level is given -- mask and no_nonZeroDepthPts (src/Frame.cpp:170-327).  Any output may be NULL.
+int ellc_ref_frame_level(const uint8_t* gray, int level, const float* depth_level, uint8_t* pyr_image, int* pyr_w, int* pyr_h,
+                         float* gradx, float* grady, uint8_t* mask, int* count) {
+    init_once();
+    frame* f = make_frame(gray);
+    const int r = H0 >> level, c = W0 >> level;
+    if (depth_level) {
+        for (int y = 0; y < r; ++y) std::memcpy(f->depth_pyramid[level].ptr<float>(y), depth_level + (size_t)y * c, (size_t)c * sizeof(float));
+    }
+    f->updationOnPyrChange(level, depth_level != nullptr);
+    const Mat& im = f->image_pyramid[level];
+    if (pyr_w) *pyr_w = im.cols;
+    if (pyr_h) *pyr_h = im.rows;
+    if (pyr_image) for (int y = 0; y < im.rows; ++y) std::memcpy(pyr_image + (size_t)y * im.cols, im.ptr<uchar>(y), (size_t)im.cols);
+    if (gradx) for (int y = 0; y < r; ++y) std::memcpy(gradx + (size_t)y * c, f->gradientx.ptr<float>(y), (size_t)c * sizeof(float));
+    if (grady) for (int y = 0; y < r; ++y) std::memcpy(grady + (size_t)y * c, f->gradienty.ptr<float>(y), (size_t)c * sizeof(float));
+    if (depth_level && mask) for (int y = 0; y < r; ++y) std::memcpy(mask + (size_t)y * c, f->mask.ptr<uchar>(y), (size_t)c);
+    if (depth_level && count) *count = f->no_nonZeroDepthPts;
+    delete f;
+    return 0;
+}
+
+// frame::getInterpolatedElement(x, y, int) on the level image and (x, y, "gradx" / "grady") on the gradients (src/Frame.h:181-394)
+int ellc_ref_interpolate(const uint8_t* gray, int level, int n, const float* xs, const float* ys, float* intensity, float* gx, float* gy) {
+    init_once();
+    frame* f = make_frame(gray);
+    f->updationOnPyrChange(level, false);
+    for (int i = 0; i < n; ++i) {
+        intensity[i] = f->getInterpolatedElement(xs[i], ys[i], 1);
+        gx[i] = f->getInterpolatedElement(xs[i], ys[i], "gradx");
+        gy[i] = f->getInterpolatedElement(xs[i], ys[i], "grady");
+    }
+    delete f;
+    return 0;
+}
+
+// frame::concatenateRelativePose / concatenateOriginPose (src/Frame.cpp:503-562)
+void ellc_ref_concat_relative(const float a[6], const float b[6], float dest[6]) {
+    frame f;
+    float x[6], y[6];
+    std::memcpy(x, a, sizeof(x)); std::memcpy(y, b, sizeof(y));
+    f.concatenateRelativePose(x, y, dest);
+}
+void ellc_ref_concat_origin(const float a[6], const float b[6], float dest[6]) {
+    frame f;
+    float x[6], y[6];
+    std::memcpy(x, a, sizeof(x)); std::memcpy(y, b, sizeof(y));
+    f.concatenateOriginPose(x, y, dest);
+}
+
+// The reference's driver, untouched: GetImagePoseEstimate(keyframe, frame, ..., t-1 frame, ...) (src/ImageFunc.cpp:49-315).
+// The keyframe sits at the world origin; the t-1 frame carries tminus1_pose_wrt_world, from which the driver derives its
+// initial pose (:97-108).  Returns the relative pose and the frame's poseWrtOrigin / poseWrtWorld post-conditions (:305-307).
+int ellc_ref_get_image_pose_estimate(const uint8_t* kf_gray, const uint8_t* cur_gray, const float* const* depth, const float* const* var,
+                                     const float tminus1_pose_wrt_world[6], float pose_out[6], float pose_wrt_origin[6],
+                                     float pose_wrt_world[6]) {
+    init_once();
+    frame* kf = make_frame(kf_gray);
+    frame* cur = make_frame(cur_gray);
+    frame* tm1 = make_frame(cur_gray);
+    DepthHolder dh;
+    set_keyframe_depth(kf, dh, depth, var);
+    for (int i = 0; i < 6; ++i) tm1->poseWrtWorld[i] = tminus1_pose_wrt_world[i];
+    float unused[6] = {0, 0, 0, 0, 0, 0};
+    std::vector<float> p = GetImagePoseEstimate(kf, cur, 1, dh.dm, tm1, unused, false, false);
+    for (int i = 0; i < 6; ++i) { pose_out[i] = p[i]; pose_wrt_origin[i] = cur->poseWrtOrigin[i]; pose_wrt_world[i] = cur->poseWrtWorld[i]; }
+    delete kf; delete cur; delete tm1;
+    return 0;
+}
+
+// The same level / iteration schedule (src/ImageFunc.cpp:150-299) driven from here, so that the per-iteration state of the
+// reference's PixelWisePyramid object can be recorded: hessian, sd_param, weightedPose, pose (public members,
+// src/PixelWisePyramid.h:38-107).  weight_l0 (may be NULL): display_weightimg of the last executed level-0 iteration (:361).
+int ellc_ref_track_trace(const uint8_t* kf_gray, const uint8_t* cur_gray, const float* const* depth, const float* const* var,
+                         const float init_pose[6], ellc_ref_trace* out, float* weight_l0) {
+    init_once();
+    std::memset(out, 0, sizeof(*out));
+    frame* kf = make_frame(kf_gray);
+    frame* cur = make_frame(cur_gray);
+    DepthHolder dh;
+    set_keyframe_depth(kf, dh, depth, var);
+    float pose[6];
+    for (int i = 0; i < 6; ++i) pose[i] = init_pose[i];
+    for (int level = util::MAX_PYRAMID_LEVEL - 1; level >= 0; --level) {
+        kf->updationOnPyrChange(level);
+        cur->updationOnPyrChange(level, false);
+        PixelWisePyramid wp(kf, cur, pose, dh.dm);
+        wp.putPreviousPose(cur);
+        wp.pose = pose;
+        out->n_selected[level] = kf->no_nonZeroDepthPts;
+        for (int iter = 0; iter < util::MAX_ITER[level]; ++iter) {
+            wp.calculatePixelWiseParallel();
+            ellc_ref_iter& r = out->it[level][iter];
+            for (int i = 0; i < 6; ++i)
+                for (int j = 0; j < 6; ++j) r.H[i * 6 + j] = wp.hessian.at<float>(i, j);
+            for (int i = 0; i < 6; ++i) { r.b[i] = wp.sd_param.at<float>(0, i); r.pose_after[i] = pose[i]; }
+            r.weighted_pose = wp.weightedPose;
+            out->n_iters[level] = iter + 1;
+            if (level == 0 && weight_l0)
+                for (int y = 0; y < H0; ++y) std::memcpy(weight_l0 + (size_t)y * W0, wp.display_weightimg.ptr<float>(y), (size_t)W0 * sizeof(float));
+            if (wp.weightedPose < 1.0f) break;                     // src/ImageFunc.cpp:251-252
+        }
+    }
+    for (int i = 0; i < 6; ++i) out->final_pose[i] = pose[i];
+    delete kf; delete cur;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,147 @@
+"""ctypes binding of oracle/_ref/libellc_ref.so: the REFERENCE'S OWN tracking sources (src/Frame.cpp, PixelWisePyramid.cpp,
+Pyramid.cpp, UserDefinedFunc.cpp, ImageFunc.cpp, compiled where they lie under /root/reference against the stand-in headers
+of oracle/shim/; recipe: oracle/Makefile, driver: oracle/ref_driver.cpp).  Test infrastructure only: it pins the oracle
+restatement on the reference's own per-pixel code and driver.  The library is git-ignored and travels to the GPU box as a
+built file; /root/reference is needed only to (re)build it."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_ref", "libellc_ref.so")
+REFERENCE_SRC = "/root/reference/src"
+LEVELS = 4
+MAX_ITERS = 12
+
+
+def available():
+    """True if the library exists or can be built here (the reference sources are mounted)."""
+    return os.path.exists(_SO) or os.path.isdir(REFERENCE_SRC)
+
+
+def build(force=False):
+    if not os.path.isdir(REFERENCE_SRC):
+        if os.path.exists(_SO):
+            return _SO
+        raise RuntimeError("oracle/_ref/libellc_ref.so is missing and /root/reference is not mounted")
+    deps = [os.path.join(_HERE, "ref_driver.cpp")]
+    for root, _, files in os.walk(os.path.join(_HERE, "shim")):
+        deps += [os.path.join(root, f) for f in files]
+    stale = (not os.path.exists(_SO)) or any(os.path.getmtime(p) > os.path.getmtime(_SO) for p in deps)
+    if force or stale:
+        subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
+    return _SO
+
+
+class Iter(C.Structure):
+    _fields_ = [("H", C.c_float * 36), ("b", C.c_float * 6), ("weighted_pose", C.c_float), ("pose_after", C.c_float * 6),
+                ("pad_", C.c_float)]
+
+
+class Trace(C.Structure):
+    _fields_ = [("n_selected", C.c_int * LEVELS), ("n_iters", C.c_int * LEVELS), ("it", (Iter * MAX_ITERS) * LEVELS),
+                ("final_pose", C.c_float * 6)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f6(v):
+    return np.ascontiguousarray(np.asarray(v, dtype=np.float32).reshape(6))
+
+
+def dims():
+    """The reference's compile-time size and intrinsics (src/ExternVariable.h:39-59)."""
+    w, h = C.c_int(), C.c_int()
+    fx, fy, cx, cy = C.c_float(), C.c_float(), C.c_float(), C.c_float()
+    lib().ellc_ref_dims(C.byref(w), C.byref(h), C.byref(fx), C.byref(fy), C.byref(cx), C.byref(cy))
+    return dict(width=w.value, height=h.value, fx=np.float32(fx.value), fy=np.float32(fy.value), cx=np.float32(cx.value),
+                cy=np.float32(cy.value))
+
+
+def frame_level(image, level, depth_level=None):
+    """frame construction + updationOnPyrChange(level): pyramid image, gradients, (mask, count) if a depth level is given."""
+    d = dims()
+    image = np.ascontiguousarray(image, np.uint8)
+    assert image.shape == (d["height"], d["width"])
+    r, c = d["height"] >> level, d["width"] >> level
+    pyr = np.zeros((d["height"], d["width"]), np.uint8)
+    pw, ph, cnt = C.c_int(), C.c_int(), C.c_int()
+    gx = np.zeros((r, c), np.float32); gy = np.zeros((r, c), np.float32); mask = np.zeros((r, c), np.uint8)
+    dl = None if depth_level is None else np.ascontiguousarray(depth_level, np.float32)
+    lib().ellc_ref_frame_level(_p(image), level, _p(dl), _p(pyr), C.byref(pw), C.byref(ph), _p(gx), _p(gy), _p(mask), C.byref(cnt))
+    out = dict(image=pyr.reshape(-1)[:pw.value * ph.value].reshape(ph.value, pw.value).copy(), gradx=gx, grady=gy)
+    if dl is not None:
+        out.update(mask=mask, count=cnt.value)
+    return out
+
+
+def interpolate(image, level, xs, ys):
+    xs = np.ascontiguousarray(xs, np.float32); ys = np.ascontiguousarray(ys, np.float32)
+    image = np.ascontiguousarray(image, np.uint8)
+    n = len(xs)
+    i = np.zeros(n, np.float32); gx = np.zeros(n, np.float32); gy = np.zeros(n, np.float32)
+    lib().ellc_ref_interpolate(_p(image), level, n, _p(xs), _p(ys), _p(i), _p(gx), _p(gy))
+    return i, gx, gy
+
+
+def concat_relative(a, b):
+    out = np.empty(6, np.float32)
+    lib().ellc_ref_concat_relative(_p(_f6(a)), _p(_f6(b)), _p(out))
+    return out
+
+
+def concat_origin(a, b):
+    out = np.empty(6, np.float32)
+    lib().ellc_ref_concat_origin(_p(_f6(a)), _p(_f6(b)), _p(out))
+    return out
+
+
+def _pyr_ptrs(arrs):
+    a = [np.ascontiguousarray(x, np.float32) for x in arrs]
+    return a, (C.c_void_p * LEVELS)(*[_p(x) for x in a])
+
+
+def get_image_pose_estimate(kf_image, cur_image, depth_pyr, var_pyr, tminus1_pose_wrt_world):
+    """The reference's own driver (src/ImageFunc.cpp:49-315).  Returns (relative pose, poseWrtOrigin, poseWrtWorld)."""
+    kf_image = np.ascontiguousarray(kf_image, np.uint8); cur_image = np.ascontiguousarray(cur_image, np.uint8)
+    d, dp = _pyr_ptrs(depth_pyr); v, vp = _pyr_ptrs(var_pyr)
+    pose = np.empty(6, np.float32); po = np.empty(6, np.float32); pw = np.empty(6, np.float32)
+    lib().ellc_ref_get_image_pose_estimate(_p(kf_image), _p(cur_image), dp, vp, _p(_f6(tminus1_pose_wrt_world)), _p(pose), _p(po), _p(pw))
+    return pose, po, pw
+
+
+def track_trace(kf_image, cur_image, depth_pyr, var_pyr, init_pose, want_weights=False):
+    """Level / iteration schedule of src/ImageFunc.cpp:150-299 on the reference's PixelWisePyramid object, recording its public
+    per-iteration state (hessian, sd_param, weightedPose, pose)."""
+    kf_image = np.ascontiguousarray(kf_image, np.uint8); cur_image = np.ascontiguousarray(cur_image, np.uint8)
+    d, dp = _pyr_ptrs(depth_pyr); v, vp = _pyr_ptrs(var_pyr)
+    tr = Trace()
+    dm = dims()
+    w = np.zeros((dm["height"], dm["width"]), np.float32) if want_weights else None
+    lib().ellc_ref_track_trace(_p(kf_image), _p(cur_image), dp, vp, _p(_f6(init_pose)), C.byref(tr), _p(w))
+    levels = []
+    for l in range(LEVELS):
+        its = []
+        for k in range(tr.n_iters[l]):
+            it = tr.it[l][k]
+            its.append(dict(H=np.array(it.H, np.float32).reshape(6, 6), b=np.array(it.b, np.float32),
+                            weighted_pose=np.float32(it.weighted_pose), pose_after=np.array(it.pose_after, np.float32)))
+        levels.append(its)
+    out = dict(n_selected=list(tr.n_selected), n_iters=list(tr.n_iters), levels=levels, final_pose=np.array(tr.final_pose, np.float32))
+    if want_weights:
+        out["weights_l0"] = w
+    return out

@@ -1,0 +1,76 @@
+"""Generates tests/golden/reference_track_480x270.npz from THE REFERENCE'S OWN CODE (run in the build container, where
+/root/reference is mounted): oracle/_ref/libellc_ref.so = the reference's unmodified src/Frame.cpp, PixelWisePyramid.cpp,
+UserDefinedFunc.cpp, ImageFunc.cpp ... compiled against the stand-in headers under oracle/shim/ (oracle/ref_driver.cpp).
+
+The fixture holds seeded inputs at the reference's compiled-in configuration (480x270, its intrinsics) and, for every pair,
+what the reference produced: per-level selected-pixel counts and iteration counts, hessian / sd_param / weightedPose / pose
+of every iteration, display_weightimg of the last level-0 iteration, the result of GetImagePoseEstimate() and its
+poseWrtOrigin / poseWrtWorld post-conditions.  tests/test_reference_pin.py checks the oracle against it (CPU) and
+tests/test_gpu_parity.py the CUDA path (GPU box, where /root/reference does not exist).
+
+    python tests/golden/make_reference_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+
+def reference_case(n_frames=3, seed=31):
+    """Keyframe + frames at the reference's compiled-in size and intrinsics; the last frame is a large rotation (out-of-bounds
+    warps, more iterations)."""
+    from egomotion_with_local_loop_closures_b200 import synth
+    from oracle import refbinding as ref
+    k = ref.dims()
+    kk = dict(fx=k["fx"], fy=k["fy"], cx=k["cx"], cy=k["cy"])
+    scene = synth.SynthScene(k["width"], k["height"], k=kk)
+    kf = scene.keyframe(noise_seed=seed)
+    rng = np.random.default_rng(seed)
+    frames, gt = [], []
+    for i in range(n_frames):
+        big = (i == n_frames - 1)
+        p = synth.random_pose(rng, rot=np.deg2rad(3.5 if big else 1.2), trans=0.04 if big else 0.015)
+        frames.append(scene.render(synth.se3_exp(p), noise_seed=seed * 100 + i))
+        gt.append(p.astype(np.float32))
+    return dict(k=k, kf=kf, frames=frames, gt=gt)
+
+
+def main():
+    from oracle import refbinding as ref
+    case = reference_case()
+    k, kf = case["k"], case["kf"]
+    out = dict(width=np.array([k["width"]]), height=np.array([k["height"]]),
+               intr=np.array([k["fx"], k["fy"], k["cx"], k["cy"]], np.float32), kf_image=kf["image"],
+               frames=np.stack(case["frames"]), gt=np.stack(case["gt"]))
+    for l in range(4):
+        out[f"depth{l}"] = kf["depth"][l]
+        out[f"var{l}"] = kf["var"][l]
+    inits = [np.zeros(6, np.float32), (case["gt"][1] * 0.6).astype(np.float32), np.zeros(6, np.float32)]
+    out["init"] = np.stack(inits)
+    for i, (fr, init) in enumerate(zip(case["frames"], inits)):
+        tr = ref.track_trace(kf["image"], fr, kf["depth"], kf["var"], init, want_weights=True)
+        out[f"p{i}_n_selected"] = np.array(tr["n_selected"], np.int32)
+        out[f"p{i}_n_iters"] = np.array(tr["n_iters"], np.int32)
+        out[f"p{i}_pose"] = tr["final_pose"]
+        out[f"p{i}_weights_l0"] = tr["weights_l0"]
+        for l in range(4):
+            its = tr["levels"][l]
+            out[f"p{i}_H_{l}"] = np.stack([it["H"] for it in its])
+            out[f"p{i}_b_{l}"] = np.stack([it["b"] for it in its])
+            out[f"p{i}_wp_{l}"] = np.array([it["weighted_pose"] for it in its], np.float32)
+            out[f"p{i}_pose_{l}"] = np.stack([it["pose_after"] for it in its])
+        # the reference's own driver: the t-1 frame's world pose is its initialisation (src/ImageFunc.cpp:97-108)
+        pose, po, pw = ref.get_image_pose_estimate(kf["image"], fr, kf["depth"], kf["var"], init)
+        out[f"p{i}_driver_pose"] = pose
+        out[f"p{i}_driver_pose_wrt_origin"] = po
+        out[f"p{i}_driver_pose_wrt_world"] = pw
+    path = os.path.join(HERE, "reference_track_480x270.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,185 @@
+"""The oracle restatement against THE REFERENCE'S OWN CODE.
+
+oracle/_ref/libellc_ref.so is the reference's unmodified src/Frame.cpp, PixelWisePyramid.cpp, Pyramid.cpp, UserDefinedFunc.cpp
+and ImageFunc.cpp, compiled where they lie under /root/reference against the stand-in OpenCV / Eigen / Boost headers of
+oracle/shim/ (oracle/ref_driver.cpp, `make -C oracle ref`).  tests/golden/reference_track_480x270.npz holds what that library
+produced on seeded inputs at the reference's compiled-in configuration (generator: tests/golden/make_reference_golden.py).
+
+  * fixture tests run everywhere (the fixture is committed);
+  * live tests run where the library exists or can be built (this container: /root/reference is mounted).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import refbinding as ref
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+live = pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libellc_ref.so not built and /root/reference not mounted")
+
+
+@pytest.fixture(scope="module")
+def fx():
+    return np.load(os.path.join(GOLD, "reference_track_480x270.npz"))
+
+
+def _ocfg(oracle_mod, g, **over):
+    fxv, fyv, cx, cy = (float(v) for v in g["intr"])
+    return oracle_mod.default_config(int(g["width"][0]), int(g["height"][0]), fx=fxv, fy=fyv, cx=cx, cy=cy, **over)
+
+
+def _depth(g):
+    return [g[f"depth{l}"] for l in range(4)], [g[f"var{l}"] for l in range(4)]
+
+
+def test_oracle_is_bit_identical_to_the_reference_trace(oracle_mod, fx):
+    """Every iteration of every level: hessian, sd_param, weightedPose and the updated pose of the reference's
+    PixelWisePyramid object (src/PixelWisePyramid.h:38-107) are BIT-IDENTICAL to the oracle's; so are the selected-pixel
+    counts, the iteration counts (early-out, src/ImageFunc.cpp:251-252) and the final pose.  480x270 is not divisible by 8,
+    so the reference's `height/2^L` vs pyrDown `(h+1)/2` quirk (src/Frame.cpp:110-112, :321-322) is exercised."""
+    g = fx
+    ocfg = _ocfg(oracle_mod, g)
+    depth, var = _depth(g)
+    n_pairs = len(g["frames"])
+    total_iters = 0
+    for i in range(n_pairs):
+        pose, tr = oracle_mod.track(ocfg, g["kf_image"], g["frames"][i], depth, var, g["init"][i])
+        assert tr["n_selected"] == list(g[f"p{i}_n_selected"])
+        assert tr["n_iters"] == list(g[f"p{i}_n_iters"])
+        assert np.array_equal(pose, g[f"p{i}_pose"])
+        for l in range(4):
+            its = tr["levels"][l]
+            assert np.array_equal(np.stack([it["H"] for it in its]).reshape(-1, 6, 6), g[f"p{i}_H_{l}"]), (i, l)
+            assert np.array_equal(np.stack([it["b"] for it in its]), g[f"p{i}_b_{l}"]), (i, l)
+            assert np.array_equal(np.array([it["weighted_pose"] for it in its], np.float32), g[f"p{i}_wp_{l}"]), (i, l)
+            assert np.array_equal(np.stack([it["pose_after"] for it in its]), g[f"p{i}_pose_{l}"]), (i, l)
+            total_iters += len(its)
+    assert total_iters >= 40                                      # the large-rotation pair runs many iterations
+    assert np.abs(g["p0_pose"] - g["gt"][0]).max() < 2e-3         # and the reference does track the synthetic scene
+
+
+def test_oracle_weight_image_is_bit_identical_to_the_reference(oracle_mod, fx):
+    """display_weightimg of the last executed level-0 iteration (src/PixelWisePyramid.cpp:334-361): per-pixel Huber x
+    variance weights, 0 for unselected and out-of-bounds pixels."""
+    g = fx
+    ocfg = _ocfg(oracle_mod, g)
+    depth, var = _depth(g)
+    kpyr = oracle_mod.image_pyramid(g["kf_image"])
+    for i in range(len(g["frames"])):
+        poses0 = g[f"p{i}_pose_0"]
+        before = poses0[-2] if len(poses0) > 1 else g[f"p{i}_pose_1"][-1]          # pose the last level-0 iteration started from
+        cpyr = oracle_mod.image_pyramid(g["frames"][i])
+        o = oracle_mod.gn_evaluate(ocfg, 0, kpyr[0], cpyr[0], depth[0], var[0], before, want_weights=True)
+        assert np.array_equal(o["weights"], g[f"p{i}_weights_l0"]), i
+        assert np.array_equal(np.asarray(o["H"], np.float32).reshape(6, 6), g[f"p{i}_H_0"][-1]), i
+
+
+def test_oracle_matches_the_reference_driver(oracle_mod, fx):
+    """GetImagePoseEstimate itself (src/ImageFunc.cpp:49-315): initial pose = log(exp(t-1 world pose) exp(keyframe world
+    pose)^-1) (:97-108), result, and the poseWrtOrigin / poseWrtWorld post-conditions (:305-307)."""
+    g = fx
+    ocfg = _ocfg(oracle_mod, g)
+    depth, var = _depth(g)
+    zero = np.zeros(6, np.float32)
+    for i in range(len(g["frames"])):
+        init = oracle_mod.concat_origin(g["init"][i], zero)
+        pose, _ = oracle_mod.track(ocfg, g["kf_image"], g["frames"][i], depth, var, init, want_trace=False)
+        assert np.array_equal(pose, g[f"p{i}_driver_pose"]), i
+        assert np.array_equal(oracle_mod.concat_relative(pose, zero), g[f"p{i}_driver_pose_wrt_origin"]), i
+        assert np.array_equal(oracle_mod.concat_relative(pose, zero), g[f"p{i}_driver_pose_wrt_world"]), i
+
+
+# ---- live: the library itself (this container) ----------------------------------------------------------------------------
+@live
+def test_fixture_is_what_the_reference_produces(fx):
+    g = fx
+    depth, var = _depth(g)
+    k = ref.dims()
+    assert (k["width"], k["height"]) == (int(g["width"][0]), int(g["height"][0]))
+    assert np.array_equal(np.array([k["fx"], k["fy"], k["cx"], k["cy"]], np.float32), g["intr"])
+    tr = ref.track_trace(g["kf_image"], g["frames"][1], depth, var, g["init"][1], want_weights=True)
+    assert tr["n_iters"] == list(g["p1_n_iters"]) and np.array_equal(tr["final_pose"], g["p1_pose"])
+    assert np.array_equal(tr["weights_l0"], g["p1_weights_l0"])
+    pose, po, pw = ref.get_image_pose_estimate(g["kf_image"], g["frames"][1], depth, var, g["init"][1])
+    assert np.array_equal(pose, g["p1_driver_pose"]) and np.array_equal(po, g["p1_driver_pose_wrt_origin"])
+
+
+@live
+def test_reference_stages_vs_oracle(oracle_mod, fx):
+    """constructImagePyramids / calculateGradient / calculateNonZeroDepthPts (src/Frame.cpp:170-327) on every level, incl. NaN,
+    negative and -0 depths."""
+    g = fx
+    depth, _ = _depth(g)
+    opyr = oracle_mod.image_pyramid(g["frames"][0])
+    rng = np.random.default_rng(3)
+    for l in range(4):
+        d = depth[l].copy()
+        idx = rng.integers(0, d.size, 40)
+        d.reshape(-1)[idx[:10]] = np.nan; d.reshape(-1)[idx[10:20]] = -1.0; d.reshape(-1)[idx[20:30]] = -0.0; d.reshape(-1)[idx[30:]] = np.inf
+        r = ref.frame_level(g["frames"][0], l, d)
+        assert np.array_equal(r["image"], opyr[l]), l
+        rows, cols = d.shape
+        ogx, ogy = oracle_mod.gradient(opyr[l], rows, cols)
+        assert np.array_equal(r["gradx"], ogx) and np.array_equal(r["grady"], ogy), l
+        omask, ocount = oracle_mod.mask_count(d)
+        assert np.array_equal(r["mask"], omask) and r["count"] == ocount, l
+
+
+@live
+def test_reference_samplers_vs_oracle(oracle_mod, fx):
+    """frame::getInterpolatedElement (src/Frame.h:181-394) at random, integer, border and out-of-bounds coordinates."""
+    g = fx
+    img = g["frames"][0]
+    rng = np.random.default_rng(9)
+    for l in (0, 2, 3):
+        rows, cols = img.shape[0] >> l, img.shape[1] >> l
+        xs = np.concatenate([rng.uniform(-3, cols + 3, 400), rng.integers(-2, cols + 2, 100).astype(np.float64),
+                             [0, cols - 1, cols - 1 + 1e-4, cols - 0.5, -1e-6, -0.5, cols, 0.5]]).astype(np.float32)
+        ys = np.concatenate([rng.uniform(-3, rows + 3, 400), rng.integers(-2, rows + 2, 100).astype(np.float64),
+                             [0, rows - 1, rows - 1 + 1e-4, rows - 0.5, -1e-6, 2.0, 3.0, rows]]).astype(np.float32)
+        ri, rgx, rgy = ref.interpolate(img, l, xs, ys)
+        lvl = oracle_mod.image_pyramid(img)[l]
+        ogx, ogy = oracle_mod.gradient(lvl, rows, cols)
+        oi = np.array([oracle_mod.interp_u8(lvl, x, y, 1, rows, cols) for x, y in zip(xs, ys)], np.float32)
+        ox = np.array([oracle_mod.interp_f32(ogx, x, y) for x, y in zip(xs, ys)], np.float32)
+        oy = np.array([oracle_mod.interp_f32(ogy, x, y) for x, y in zip(xs, ys)], np.float32)
+        assert np.array_equal(ri, oi) and np.array_equal(rgx, ox) and np.array_equal(rgy, oy), l
+        assert (ri == -1).sum() > 5 and (ri > 0).sum() > 200
+
+
+@live
+def test_reference_pose_algebra_vs_oracle(oracle_mod):
+    """frame::concatenateRelativePose / concatenateOriginPose (src/Frame.cpp:503-562)."""
+    rng = np.random.default_rng(4)
+    for n in range(60):
+        s = 10.0 ** rng.uniform(-3, 0.3)
+        a = (rng.standard_normal(6) * s).astype(np.float32); b = (rng.standard_normal(6) * s).astype(np.float32)
+        assert np.array_equal(ref.concat_relative(a, b), oracle_mod.concat_relative(a, b)), n
+        assert np.array_equal(ref.concat_origin(a, b), oracle_mod.concat_origin(a, b)), n
+
+
+@live
+def test_reference_live_random_pairs(oracle_mod):
+    """Fresh seeds (not the fixture's): the oracle stays bit-identical to the reference, including an all-out-of-bounds start
+    (zero step: H = 0, cv::Mat::inv() returns zeros) and a keyframe without depth."""
+    import sys
+    sys.path.insert(0, os.path.join(GOLD))
+    from make_reference_golden import reference_case
+    case = reference_case(n_frames=2, seed=77)
+    k, kf = case["k"], case["kf"]
+    ocfg = oracle_mod.default_config(k["width"], k["height"], fx=float(k["fx"]), fy=float(k["fy"]), cx=float(k["cx"]), cy=float(k["cy"]))
+    far = np.array([0, 0, 0, 50.0, 0, 0], np.float32)                                        # every warp lands outside the image
+    nodepth = [np.zeros_like(d) for d in kf["depth"]]
+    runs = [(case["frames"][0], kf["depth"], np.zeros(6, np.float32)), (case["frames"][1], kf["depth"], (case["gt"][1] * 0.5).astype(np.float32)),
+            (case["frames"][0], kf["depth"], far), (case["frames"][0], nodepth, np.zeros(6, np.float32))]
+    for n, (fr, depth, init) in enumerate(runs):
+        pose, tr = oracle_mod.track(ocfg, kf["image"], fr, depth, kf["var"], init)
+        r = ref.track_trace(kf["image"], fr, depth, kf["var"], init)
+        assert tr["n_selected"] == r["n_selected"] and tr["n_iters"] == r["n_iters"], n
+        assert np.array_equal(pose, r["final_pose"]), n
+        for l in range(4):
+            for o, q in zip(tr["levels"][l], r["levels"][l]):
+                assert np.array_equal(np.asarray(o["H"], np.float32).reshape(6, 6), q["H"]) and np.array_equal(o["b"], q["b"]), (n, l)
+                assert np.float32(o["weighted_pose"]) == q["weighted_pose"], (n, l)
+    assert tr["n_iters"] == [1, 1, 1, 1]                          # no depth: one zero step per level
