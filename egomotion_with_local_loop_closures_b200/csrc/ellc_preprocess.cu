@@ -350,7 +350,8 @@ accumulate_weights_kernel(float* __restrict__ kf_w, const uint8_t* __restrict__ 
     kf_w[i] = w;
 }
 
-// frame::finaliseWeights, src/Frame.cpp:678-695: weight_pyramid[level] /= numWeightsAdded[level] when it is > 0
+// frame::finaliseWeights, src/Frame.cpp:678-695: weight_pyramid[level] = weight_pyramid[level] / numWeightsAdded[level] when it
+// is > 0.  cv::Mat / scalar multiplies by the reciprocal (MatOp_AddEx with alpha = 1./s, applied in float), it does not divide.
 struct Counts4 { int c[kLevels]; };
 __global__ void __launch_bounds__(256) finalise_weights_kernel(float* __restrict__ kf_w, Counts4 cnt, Geometry geo) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -358,7 +359,7 @@ __global__ void __launch_bounds__(256) finalise_weights_kernel(float* __restrict
     int level = 0;
 #pragma unroll
     for (int l = 1; l < kLevels; ++l) level += (i >= geo.win_off[l]);
-    if (cnt.c[level] > 0) kf_w[i] = __fdiv_rn(kf_w[i], (float)cnt.c[level]);
+    if (cnt.c[level] > 0) kf_w[i] = __fmul_rn(kf_w[i], (float)(1.0 / (double)cnt.c[level]));
 }
 
 // precomputePixelWiseInvCompositional (:561-680) for the selected pixels of one keyframe level, in selection-list order, plus

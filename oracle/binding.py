@@ -301,8 +301,11 @@ def accumulate_weights(weight_pyr, counts, weight_last):
 
 
 def finalise_weights(weight_pyr, counts):
-    """frame::finaliseWeights, src/Frame.cpp:678-695: weight_pyramid[l] /= numWeightsAdded[l] when > 0."""
-    return [(weight_pyr[l] / np.float32(counts[l])).astype(np.float32) if counts[l] > 0 else weight_pyr[l] for l in range(LEVELS)]
+    """frame::finaliseWeights, src/Frame.cpp:678-695: weight_pyramid[l] = weight_pyramid[l] / numWeightsAdded[l] when > 0.
+    cv::Mat / scalar is a multiplication by the reciprocal (matop.cpp: MatOp_AddEx with alpha = 1./s, applied by the CV_32F
+    convertTo kernel as a float multiply by (float)alpha), not a division."""
+    return [(weight_pyr[l].astype(np.float32) * np.float32(1.0 / counts[l])).astype(np.float32) if counts[l] > 0 else weight_pyr[l]
+            for l in range(LEVELS)]
 
 
 def track_lc(cfg, kf_img0, cur_img0, depth_pyr, weight_pyr, init_pose):

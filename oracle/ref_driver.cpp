@@ -234,4 +234,77 @@ int ellc_ref_track_trace(const uint8_t* kf_gray, const uint8_t* cur_gray, const 
     return 0;
 }
 
+// The reference's constant-weight loop-closure flow, end to end, with its own driver:
+//   1. FLAG_DO_CONST_WEIGHT_POSE_ESTIMATION on: every sequential GetImagePoseEstimate() saves the weights of the last iteration
+//      of each level into the keyframe (saveWeights(true), src/ImageFunc.cpp:280-288, src/PixelWisePyramid.cpp:500-552);
+//   2. frame::finaliseWeights() when the keyframe is retired (src/main.cpp:431-434, src/Frame.cpp:678-695);
+//   3. GetImagePoseEstimate(..., fromLoopClosure = true): calculatePixelWiseParallelInvCompositional (:917-974).
+// parallel selects FLAG_DO_PARALLEL_CONST_WEIGHT_POSE_EST (3 precompute bands + 2 iteration bands vs one).
+// Outputs: the finalised weight pyramid + counts, the sequential poses, the loop-closure pose from the driver, and the trace of
+// the same loop-closure track stepped from here (hessian, sd_param, weightedPose, pose per iteration).
+int ellc_ref_lc_flow(const uint8_t* kf_gray, int n_seq, const uint8_t* const* seq_gray, const float* seq_tminus1, const float* const* depth,
+                     const float* const* var, const uint8_t* lc_gray, const float lc_tminus1[6], int parallel, float* const* weight_out,
+                     int counts[4], float* seq_poses, float lc_pose[6], ellc_ref_trace* lc_trace) {
+    init_once();
+    util::FLAG_DO_CONST_WEIGHT_POSE_ESTIMATION = true;
+    util::FLAG_DO_PARALLEL_CONST_WEIGHT_POSE_EST = parallel != 0;
+    frame* kf = make_frame(kf_gray);
+    DepthHolder dh;
+    set_keyframe_depth(kf, dh, depth, var);
+    float unused[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < n_seq; ++i) {
+        frame* cur = make_frame(seq_gray[i]);
+        frame* tm1 = make_frame(seq_gray[i]);
+        for (int k = 0; k < 6; ++k) tm1->poseWrtWorld[k] = seq_tminus1[i * 6 + k];
+        std::vector<float> p = GetImagePoseEstimate(kf, cur, i + 1, dh.dm, tm1, unused, false, false);
+        for (int k = 0; k < 6; ++k) seq_poses[i * 6 + k] = p[k];
+        delete cur; delete tm1;
+    }
+    kf->finaliseWeights();
+    for (int l = 0; l < 4; ++l) {
+        const int r = H0 >> l, c = W0 >> l;
+        counts[l] = kf->numWeightsAdded[l];
+        for (int y = 0; y < r; ++y) std::memcpy(weight_out[l] + (size_t)y * c, kf->weight_pyramid[l].ptr<float>(y), (size_t)c * sizeof(float));
+    }
+    {
+        frame* cur = make_frame(lc_gray);
+        frame* tm1 = make_frame(lc_gray);
+        for (int k = 0; k < 6; ++k) tm1->poseWrtWorld[k] = lc_tminus1[k];
+        std::vector<float> p = GetImagePoseEstimate(kf, cur, n_seq + 1, dh.dm, tm1, unused, true, false);
+        for (int k = 0; k < 6; ++k) lc_pose[k] = p[k];
+        delete cur; delete tm1;
+    }
+    if (lc_trace) {
+        std::memset(lc_trace, 0, sizeof(*lc_trace));
+        frame* cur = make_frame(lc_gray);
+        float pose[6] = {0, 0, 0, 0, 0, 0}, zero[6] = {0, 0, 0, 0, 0, 0}, tm1w[6];
+        for (int k = 0; k < 6; ++k) tm1w[k] = lc_tminus1[k];
+        kf->concatenateOriginPose(tm1w, zero, pose);                            // src/ImageFunc.cpp:106
+        for (int level = util::MAX_PYRAMID_LEVEL - 1; level >= 0; --level) {
+            kf->updationOnPyrChange(level);
+            cur->updationOnPyrChange(level, false);
+            PixelWisePyramid wp(kf, cur, pose, dh.dm);
+            wp.putPreviousPose(cur);
+            wp.pose = pose;
+            lc_trace->n_selected[level] = kf->no_nonZeroDepthPts;
+            for (int iter = 0; iter < util::MAX_ITER[level]; ++iter) {
+                wp.calculatePixelWiseParallelInvCompositional(iter);
+                ellc_ref_iter& r = lc_trace->it[level][iter];
+                for (int i = 0; i < 6; ++i)
+                    for (int j = 0; j < 6; ++j) r.H[i * 6 + j] = wp.hessian.at<float>(i, j);
+                for (int i = 0; i < 6; ++i) { r.b[i] = wp.sd_param.at<float>(0, i); r.pose_after[i] = pose[i]; }
+                r.weighted_pose = wp.weightedPose;
+                lc_trace->n_iters[level] = iter + 1;
+                if (wp.weightedPose < 1.0f) break;
+            }
+        }
+        for (int i = 0; i < 6; ++i) lc_trace->final_pose[i] = pose[i];
+        delete cur;
+    }
+    delete kf;
+    util::FLAG_DO_CONST_WEIGHT_POSE_ESTIMATION = false;
+    util::FLAG_DO_PARALLEL_CONST_WEIGHT_POSE_EST = false;
+    return 0;
+}
+
 }  // extern "C"

@@ -145,3 +145,37 @@ def track_trace(kf_image, cur_image, depth_pyr, var_pyr, init_pose, want_weights
     if want_weights:
         out["weights_l0"] = w
     return out
+
+
+def _trace_dict(tr):
+    levels = []
+    for l in range(LEVELS):
+        its = []
+        for k in range(tr.n_iters[l]):
+            it = tr.it[l][k]
+            its.append(dict(H=np.array(it.H, np.float32).reshape(6, 6), b=np.array(it.b, np.float32),
+                            weighted_pose=np.float32(it.weighted_pose), pose_after=np.array(it.pose_after, np.float32)))
+        levels.append(its)
+    return dict(n_selected=list(tr.n_selected), n_iters=list(tr.n_iters), levels=levels, final_pose=np.array(tr.final_pose, np.float32))
+
+
+def lc_flow(kf_image, seq_images, seq_tminus1, depth_pyr, var_pyr, lc_image, lc_tminus1, parallel=True):
+    """The reference's constant-weight loop-closure flow with its own driver: sequential tracks saving weights,
+    frame::finaliseWeights, then GetImagePoseEstimate(fromLoopClosure=true).  Returns dict(weights, counts, seq_poses, lc_pose,
+    lc_trace)."""
+    dm = dims()
+    kf_image = np.ascontiguousarray(kf_image, np.uint8)
+    seq = [np.ascontiguousarray(a, np.uint8) for a in seq_images]
+    sp = (C.c_void_p * len(seq))(*[_p(a) for a in seq])
+    tm1 = np.ascontiguousarray(np.asarray(seq_tminus1, np.float32).reshape(len(seq), 6))
+    d, dp = _pyr_ptrs(depth_pyr); v, vp = _pyr_ptrs(var_pyr)
+    lc_image = np.ascontiguousarray(lc_image, np.uint8)
+    w = [np.zeros((dm["height"] >> l, dm["width"] >> l), np.float32) for l in range(LEVELS)]
+    wp = (C.c_void_p * LEVELS)(*[_p(a) for a in w])
+    counts = (C.c_int * LEVELS)()
+    seq_poses = np.zeros((len(seq), 6), np.float32)
+    lc_pose = np.zeros(6, np.float32)
+    tr = Trace()
+    lib().ellc_ref_lc_flow(_p(kf_image), len(seq), sp, _p(tm1), dp, vp, _p(lc_image), _p(_f6(lc_tminus1)), int(bool(parallel)), wp, counts,
+                           _p(seq_poses), _p(lc_pose), C.byref(tr))
+    return dict(weights=w, counts=list(counts), seq_poses=seq_poses, lc_pose=lc_pose, lc_trace=_trace_dict(tr))

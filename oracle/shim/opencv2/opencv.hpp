@@ -205,14 +205,9 @@ inline Mat operator*(const Mat& a, const Mat& b) {
 }
 inline Mat operator*(const Mat& a, double s) { return a.mul(s); }
 inline Mat operator*(double s, const Mat& a) { return a.mul(s); }
-inline Mat operator/(const Mat& a, double s) {
-    assert(a.depth() == CV_32F);
-    Mat m(a.rows, a.cols, a.flags);
-    const float f = (float)s;
-    for (int r = 0; r < a.rows; ++r)
-        for (int c = 0; c < a.cols; ++c) m.at<float>(r, c) = a.at<float>(r, c) / f;
-    return m;
-}
+// Mat / scalar is NOT a division in OpenCV: matop.cpp builds MatOp_AddEx with alpha = 1./s, and the assignment runs
+// convertTo(dst, type, alpha), whose CV_32F -> CV_32F kernel multiplies by (float)alpha
+inline Mat operator/(const Mat& a, double s) { return a.mul(1. / s); }
 inline Mat operator+(const Mat& a, const Mat& b) { Mat m = a.clone(); m += b; return m; }
 inline Mat operator-(const Mat& a, const Mat& b) { Mat m = a.clone(); m -= b; return m; }
 inline Mat operator-(const Mat& a) { return a.mul(-1.0); }

@@ -67,6 +67,23 @@ def main():
         out[f"p{i}_driver_pose"] = pose
         out[f"p{i}_driver_pose_wrt_origin"] = po
         out[f"p{i}_driver_pose_wrt_world"] = pw
+    # the constant-weight loop-closure flow with the reference's own driver (weights saved by the three sequential tracks,
+    # frame::finaliseWeights, GetImagePoseEstimate(fromLoopClosure=true) on the last frame); the weight pyramid itself is not
+    # stored (0.7 MB): whoever replays the flow rebuilds it
+    lc_tm1 = (case["gt"][2] * 0.7).astype(np.float32)
+    r = ref.lc_flow(kf["image"], case["frames"], inits, kf["depth"], kf["var"], case["frames"][2], lc_tm1, parallel=True)
+    out["lc_tminus1"] = lc_tm1
+    out["lc_counts"] = np.array(r["counts"], np.int32)
+    out["lc_seq_poses"] = r["seq_poses"]
+    out["lc_pose"] = r["lc_pose"]
+    out["lc_weight_sums"] = np.array([float(w.astype(np.float64).sum()) for w in r["weights"]])
+    out["lc_n_iters"] = np.array(r["lc_trace"]["n_iters"], np.int32)
+    for l in range(4):
+        its = r["lc_trace"]["levels"][l]
+        out[f"lc_H_{l}"] = np.stack([it["H"] for it in its])
+        out[f"lc_b_{l}"] = np.stack([it["b"] for it in its])
+        out[f"lc_wp_{l}"] = np.array([it["weighted_pose"] for it in its], np.float32)
+        out[f"lc_pose_{l}"] = np.stack([it["pose_after"] for it in its])
     path = os.path.join(HERE, "reference_track_480x270.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")

@@ -90,6 +90,41 @@ def test_oracle_matches_the_reference_driver(oracle_mod, fx):
         assert np.array_equal(oracle_mod.concat_relative(pose, zero), g[f"p{i}_driver_pose_wrt_world"]), i
 
 
+def _oracle_lc_weights(oracle_mod, g, ocfg):
+    depth, var = _depth(g)
+    h, w = int(g["height"][0]), int(g["width"][0])
+    wp = [np.zeros((h >> l, w >> l), np.float32) for l in range(4)]
+    cnt = [0] * 4
+    zero = np.zeros(6, np.float32)
+    poses = []
+    for i in range(len(g["frames"])):
+        pose, _, wl = oracle_mod.track_with_weights(ocfg, g["kf_image"], g["frames"][i], depth, var, oracle_mod.concat_origin(g["init"][i], zero))
+        oracle_mod.accumulate_weights(wp, cnt, wl)
+        poses.append(pose)
+    return oracle_mod.finalise_weights(wp, cnt), cnt, np.stack(poses)
+
+
+def test_oracle_loop_closure_flow_is_bit_identical_to_the_reference(oracle_mod, fx):
+    """SURVEY 8a row M with the reference's own driver: saveWeights(true) during the sequential tracks
+    (src/ImageFunc.cpp:280-288), frame::finaliseWeights (src/Frame.cpp:678-695), then the constant-weight inverse-compositional
+    tracker (src/PixelWisePyramid.cpp:561-974): precomputed hessian, sd_param, weightedPose and pose of every iteration."""
+    g = fx
+    ocfg = _ocfg(oracle_mod, g, lc_parallel=1)
+    depth, _ = _depth(g)
+    wf, cnt, seq_poses = _oracle_lc_weights(oracle_mod, g, ocfg)
+    assert cnt == list(g["lc_counts"]) and np.array_equal(seq_poses, g["lc_seq_poses"])
+    assert np.array_equal(np.array([float(w.astype(np.float64).sum()) for w in wf]), g["lc_weight_sums"])
+    init = oracle_mod.concat_origin(g["lc_tminus1"], np.zeros(6, np.float32))
+    pose, tr = oracle_mod.track_lc(ocfg, g["kf_image"], g["frames"][2], depth, wf, init)
+    assert tr["n_iters"] == list(g["lc_n_iters"]) and np.array_equal(pose, g["lc_pose"])
+    for l in range(4):
+        its = tr["levels"][l]
+        assert np.array_equal(np.stack([it["H"] for it in its]).reshape(-1, 6, 6), g[f"lc_H_{l}"]), l
+        assert np.array_equal(np.stack([it["b"] for it in its]), g[f"lc_b_{l}"]), l
+        assert np.array_equal(np.array([it["weighted_pose"] for it in its], np.float32), g[f"lc_wp_{l}"]), l
+        assert np.array_equal(np.stack([it["pose_after"] for it in its]), g[f"lc_pose_{l}"]), l
+
+
 # ---- live: the library itself (this container) ----------------------------------------------------------------------------
 @live
 def test_fixture_is_what_the_reference_produces(fx):
@@ -183,3 +218,25 @@ def test_reference_live_random_pairs(oracle_mod):
                 assert np.array_equal(np.asarray(o["H"], np.float32).reshape(6, 6), q["H"]) and np.array_equal(o["b"], q["b"]), (n, l)
                 assert np.float32(o["weighted_pose"]) == q["weighted_pose"], (n, l)
     assert tr["n_iters"] == [1, 1, 1, 1]                          # no depth: one zero step per level
+
+
+@live
+@pytest.mark.parametrize("parallel", [True, False])
+def test_reference_live_loop_closure_flow(oracle_mod, fx, parallel):
+    """Both settings of FLAG_DO_PARALLEL_CONST_WEIGHT_POSE_EST (3 + 2 row bands on threads / one band), a keyframe with three
+    saved weight images (1/3 is not a power of two: cv::Mat / scalar multiplies by the float reciprocal)."""
+    g = fx
+    depth, var = _depth(g)
+    ocfg = _ocfg(oracle_mod, g, lc_parallel=int(parallel))
+    r = ref.lc_flow(g["kf_image"], list(g["frames"]), g["init"], depth, var, g["frames"][1], g["gt"][1] * 0.4, parallel=parallel)
+    wf, cnt, seq_poses = _oracle_lc_weights(oracle_mod, g, ocfg)
+    assert cnt == r["counts"] and np.array_equal(seq_poses, r["seq_poses"])
+    for l in range(4):
+        assert np.array_equal(wf[l], r["weights"][l]), l
+    init = oracle_mod.concat_origin((g["gt"][1] * 0.4).astype(np.float32), np.zeros(6, np.float32))
+    pose, tr = oracle_mod.track_lc(ocfg, g["kf_image"], g["frames"][1], depth, wf, init)
+    assert np.array_equal(pose, r["lc_pose"]) and np.array_equal(pose, r["lc_trace"]["final_pose"])
+    assert tr["n_iters"] == r["lc_trace"]["n_iters"]
+    for l in range(4):
+        for o, q in zip(tr["levels"][l], r["lc_trace"]["levels"][l]):
+            assert np.array_equal(np.asarray(o["H"], np.float32).reshape(6, 6), q["H"]) and np.array_equal(o["b"], q["b"]), l
