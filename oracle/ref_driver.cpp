@@ -20,6 +20,12 @@
 #include "PixelWisePyramid.cpp"
 #include "Pyramid.cpp"
 #include "ImageFunc.cpp"
+#include "DepthPropagation.cpp"       // updateDepthImage / buildInvVarDepth / mapDepthArr2Mat / calculate_no_of_Seeds
+// (the gating helpers are private members of globalOptimize; the keyword is redefined for this one header only -- every
+// standard header it pulls in has already been included above -- so that the driver can call them without touching the source)
+#define private public
+#include "GlobalOptimize.cpp"         // calculateImageHistogram / compareImageHistogram / calculateRotationStats
+#undef private
 
 // ---- definitions that live in src/main.cpp (:34-60), which is not part of the tracking path --------------------------------
 int util::MAX_ITER[] = {4, 7, 9, 12};
@@ -304,6 +310,60 @@ int ellc_ref_lc_flow(const uint8_t* kf_gray, int n_seq, const uint8_t* const* se
     delete kf;
     util::FLAG_DO_CONST_WEIGHT_POSE_ESTIMATION = false;
     util::FLAG_DO_PARALLEL_CONST_WEIGHT_POSE_EST = false;
+    return 0;
+}
+
+// depthMap::updateDepthImage (src/DepthPropagation.cpp:1254-1315: level-0 depth from the hypotheses with the 3-pixel border rule,
+// then buildInvVarDepth :1637-1719 and mapDepthArr2Mat :1722-1746) and calculate_no_of_Seeds (:1804-1830, evaluated on the
+// input flags).  Outputs per level: keyFrame->depth_pyramid (Mat convention, 0 = invalid), deptharrptr / depthvararrptr
+// (array convention, -1 = invalid); valid_out: isValid after the call.
+int ellc_ref_update_depth_image(const uint8_t* kf_gray, const uint8_t* valid, const float* inv_depth_smoothed, const float* variance_smoothed,
+                                float* const* depth_mat, float* const* depth_arr, float* const* var_arr, uint8_t* valid_out, float* occupancy) {
+    init_once();
+    depthMap* dm = new depthMap();
+    frame* kf = make_frame(kf_gray);
+    dm->keyFrame = kf;
+    dm->currentFrame = kf;
+    const int n = W0 * H0;
+    for (int i = 0; i < n; ++i) {
+        dm->currentDepthHypothesis[i].isValid = valid[i] != 0;
+        dm->currentDepthHypothesis[i].invDepthSmoothed = inv_depth_smoothed[i];
+        dm->currentDepthHypothesis[i].varianceSmoothed = variance_smoothed[i];
+    }
+    *occupancy = dm->calculate_no_of_Seeds(true);
+    dm->updateDepthImage(false);
+    for (int i = 0; i < n; ++i) valid_out[i] = dm->currentDepthHypothesis[i].isValid ? 1 : 0;
+    for (int l = 0; l < 4; ++l) {
+        const int r = H0 >> l, c = W0 >> l;
+        for (int y = 0; y < r; ++y) std::memcpy(depth_mat[l] + (size_t)y * c, kf->depth_pyramid[l].ptr<float>(y), (size_t)c * sizeof(float));
+        std::memcpy(depth_arr[l], dm->deptharrptr[l], (size_t)r * c * sizeof(float));
+        std::memcpy(var_arr[l], dm->depthvararrptr[l], (size_t)r * c * sizeof(float));
+    }
+    delete kf;
+    delete dm;
+    return 0;
+}
+
+// globalOptimize::calculateImageHistogram (src/GlobalOptimize.cpp:40-100) and compareImageHistogram (:116-122) on two images,
+// calculateRotationStats (:419-452) on two poses.
+int ellc_ref_gating(const uint8_t* gray_a, const uint8_t* gray_b, const float pose_a[6], const float pose_b[6], float hist_a[256],
+                    float hist_b[256], double* kl_ab, float* rms_error, float* relative_view_angle) {
+    init_once();
+    globalOptimize* go = new globalOptimize("/dev/null");
+    frame* fa = make_frame(gray_a);
+    frame* fb = make_frame(gray_b);
+    go->calculateImageHistogram(fa);
+    Mat ha = go->currentLoopFrame.image_histogram.clone();
+    go->calculateImageHistogram(fb);
+    Mat hb = go->currentLoopFrame.image_histogram.clone();
+    for (int i = 0; i < 256; ++i) { hist_a[i] = ha.at<float>(i); hist_b[i] = hb.at<float>(i); }
+    *kl_ab = go->compareImageHistogram(ha, hb);
+    float pa[6], pb[6];
+    std::memcpy(pa, pose_a, sizeof(pa)); std::memcpy(pb, pose_b, sizeof(pb));
+    go->calculateRotationStats(pa, pb);
+    *rms_error = go->rms_error;
+    *relative_view_angle = go->relative_view_angle;
+    delete fa; delete fb; delete go;
     return 0;
 }
 

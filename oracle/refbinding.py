@@ -179,3 +179,28 @@ def lc_flow(kf_image, seq_images, seq_tminus1, depth_pyr, var_pyr, lc_image, lc_
     lib().ellc_ref_lc_flow(_p(kf_image), len(seq), sp, _p(tm1), dp, vp, _p(lc_image), _p(_f6(lc_tminus1)), int(bool(parallel)), wp, counts,
                            _p(seq_poses), _p(lc_pose), C.byref(tr))
     return dict(weights=w, counts=list(counts), seq_poses=seq_poses, lc_pose=lc_pose, lc_trace=_trace_dict(tr))
+
+
+def update_depth_image(kf_image, valid, inv_depth_smoothed, variance_smoothed):
+    """depthMap::updateDepthImage + buildInvVarDepth + mapDepthArr2Mat + calculate_no_of_Seeds (src/DepthPropagation.cpp)."""
+    dm = dims()
+    h, w = dm["height"], dm["width"]
+    kf_image = np.ascontiguousarray(kf_image, np.uint8)
+    valid = np.ascontiguousarray(valid, np.uint8); idep = np.ascontiguousarray(inv_depth_smoothed, np.float32)
+    vs = np.ascontiguousarray(variance_smoothed, np.float32)
+    mk = lambda: [np.zeros((h >> l, w >> l), np.float32) for l in range(LEVELS)]
+    dmat, darr, varr = mk(), mk(), mk()
+    ptrs = lambda a: (C.c_void_p * LEVELS)(*[_p(x) for x in a])
+    vout = np.zeros((h, w), np.uint8)
+    occ = C.c_float()
+    lib().ellc_ref_update_depth_image(_p(kf_image), _p(valid), _p(idep), _p(vs), ptrs(dmat), ptrs(darr), ptrs(varr), _p(vout), C.byref(occ))
+    return dict(valid_out=vout, depth=dmat, depth_arr=darr, var=varr, occupancy=occ.value)
+
+
+def gating(image_a, image_b, pose_a, pose_b):
+    """calculateImageHistogram / compareImageHistogram / calculateRotationStats (src/GlobalOptimize.cpp:40-122, :419-452)."""
+    ha = np.zeros(256, np.float32); hb = np.zeros(256, np.float32)
+    kl = C.c_double(); rms = C.c_float(); ang = C.c_float()
+    lib().ellc_ref_gating(_p(np.ascontiguousarray(image_a, np.uint8)), _p(np.ascontiguousarray(image_b, np.uint8)), _p(_f6(pose_a)),
+                          _p(_f6(pose_b)), _p(ha), _p(hb), C.byref(kl), C.byref(rms), C.byref(ang))
+    return dict(hist_a=ha, hist_b=hb, kl=kl.value, rms_error=rms.value, relative_view_angle=ang.value)

@@ -31,6 +31,9 @@
 #define CV_32FC1 CV_MAKETYPE(CV_32F, 1)
 #define CV_64FC1 CV_MAKETYPE(CV_64F, 1)
 #define CV_BGR2GRAY 6
+#define CV_GRAY2BGR 8
+#define CV_COMP_KL_DIV 5
+#define CV_8UC4 CV_MAKETYPE(CV_8U, 4)
 
 namespace cv {
 
@@ -42,6 +45,8 @@ struct Size {
     Size() : width(0), height(0) {}
     Size(int w, int h) : width(w), height(h) {}
 };
+
+struct Scalar { double val[4]; Scalar(double a = 0, double b = 0, double c = 0, double d = 0) { val[0] = a; val[1] = b; val[2] = c; val[3] = d; } };
 
 enum { DECOMP_LU = 0 };
 enum { INTER_LINEAR = 1 };
@@ -56,6 +61,15 @@ public:
     Mat() : flags(0), rows(0), cols(0), step(0), data(nullptr) {}
     Mat(int r, int c, int type) { create(r, c, type); }
     Mat(Size s, int type) { create(s.height, s.width, type); }
+    Mat(int r, int c, int type, const Scalar& v) {
+        create(r, c, type);
+        const int cn = channels();
+        for (int y = 0; y < r; ++y)
+            for (int x = 0; x < c * cn; ++x) {
+                const double q = v.val[x % cn];
+                if (depth() == CV_8U) ptr<uchar>(y)[x] = (uchar)q; else if (depth() == CV_32F) ptr<float>(y)[x] = (float)q; else ptr<double>(y)[x] = q;
+            }
+    }
     Mat(int r, int c, int type, void* ext) : flags(type), rows(r), cols(c), step((size_t)c * esz(type)), data((uchar*)ext) {}
 
     void create(int r, int c, int type) {
@@ -80,6 +94,8 @@ public:
 
     template <typename T> T* ptr(int r = 0) { return reinterpret_cast<T*>(data + (size_t)r * step); }
     template <typename T> const T* ptr(int r = 0) const { return reinterpret_cast<const T*>(data + (size_t)r * step); }
+    template <typename T> T& at(int i) { return rows == 1 ? ptr<T>(0)[i] : ptr<T>(i)[0]; }        // vector-shaped Mat
+    template <typename T> const T& at(int i) const { return rows == 1 ? ptr<T>(0)[i] : ptr<T>(i)[0]; }
     template <typename T> T& at(int r, int c) { return ptr<T>(r)[c]; }
     template <typename T> const T& at(int r, int c) const { return ptr<T>(r)[c]; }
 
@@ -347,6 +363,50 @@ inline Mat getOptimalNewCameraMatrix(const Mat&, const Mat&, Size, double) {
 }
 inline void undistort(const Mat&, Mat&, const Mat&, const Mat&, const Mat&) {
     std::fprintf(stderr, "shim: undistort is not available\n"); std::abort();
+}
+
+typedef Mat MatND;
+inline int cvRound(double v) { return (int)std::lrint(v); }
+struct Point { int x, y; Point() : x(0), y(0) {} Point(int xx, int yy) : x(xx), y(yy) {} };
+enum { COLORMAP_JET = 2 };
+// drawing / colour maps: display only, never on a compared path
+inline void applyColorMap(const Mat& src, Mat& dst, int) { dst = Mat(src.rows, src.cols, CV_8UC3); }
+inline void line(Mat&, Point, Point, const Scalar&, int = 1, int = 8, int = 0) {}
+inline void rectangle(Mat&, Point, Point, const Scalar&, int = 1, int = 8, int = 0) {}
+inline void circle(Mat&, Point, int, const Scalar&, int = 1, int = 8, int = 0) {}
+inline void putText(Mat&, const String&, Point, int, double, Scalar, int = 1, int = 8, bool = false) {}
+
+// cv::calcHist as the reference calls it (src/GlobalOptimize.cpp:68): one CV_8UC1 image, no mask, `hsize` uniform bins over
+// [ranges[0][0], ranges[0][1]), float counts in an hsize x 1 Mat
+inline void calcHist(const Mat* images, int nimages, const int* channels, const Mat& mask, Mat& hist, int dims, const int* histSize,
+                     const float** ranges, bool uniform = true, bool accumulate = false) {
+    assert(nimages == 1 && dims == 1 && uniform && !accumulate && images[0].type() == CV_8UC1 && mask.empty());
+    (void)channels; (void)nimages; (void)dims; (void)uniform; (void)accumulate;
+    const int n = histSize[0];
+    const double lo = ranges[0][0], hi = ranges[0][1];
+    Mat h(n, 1, CV_32FC1);
+    for (int y = 0; y < images[0].rows; ++y)
+        for (int x = 0; x < images[0].cols; ++x) {
+            const double v = images[0].at<uchar>(y, x);
+            if (v < lo || v >= hi) continue;
+            const int b = std::min(n - 1, (int)std::floor((v - lo) * n / (hi - lo)));
+            h.at<float>(b, 0) += 1.f;
+        }
+    hist = h;
+}
+// cv::compareHist(CV_COMP_KL_DIV) on CV_32F histograms: sum p log(p / q) in double, skipping bins where p or q is (nearly) zero
+inline double compareHist(const Mat& H1, const Mat& H2, int method) {
+    assert(method == CV_COMP_KL_DIV && H1.depth() == CV_32F && H2.depth() == CV_32F && H1.total() == H2.total());
+    (void)method;
+    double result = 0;
+    for (int r = 0; r < H1.rows; ++r)
+        for (int c = 0; c < H1.cols; ++c) {
+            const double p = H1.at<float>(r, c), q = H2.at<float>(r, c);
+            if (std::fabs(p) <= 2.2204460492503131e-16) continue;
+            const double qq = std::fabs(q) <= 2.2204460492503131e-16 ? 1e-10 : q;
+            result += p * std::log(p / qq);
+        }
+    return result;
 }
 
 // The driver hands images to frame::frame(VideoCapture) through this stand-in.

@@ -38,6 +38,23 @@ def reference_case(n_frames=3, seed=31):
     return dict(k=k, kf=kf, frames=frames, gt=gt)
 
 
+def hypotheses_case(h, w, seed=8):
+    """Seeded depth hypotheses (isValid / invDepthSmoothed / varianceSmoothed) with the awkward values: inverse depths below the
+    -0.05 gate, slightly negative, zero (depth = inf) and denormal-small."""
+    rng = np.random.default_rng(seed)
+    valid = (rng.random((h, w)) < 0.35).astype(np.uint8)
+    idep = rng.uniform(0.3, 2.0, (h, w)).astype(np.float32)
+    for value, count in ((-0.2, 200), (-0.01, 200), (0.0, 50), (1e-30, 50)):
+        idep.reshape(-1)[rng.integers(0, h * w, count)] = value
+    var = rng.uniform(1e-4, 0.05, (h, w)).astype(np.float32)
+    return valid, idep, var
+
+
+def digest(a):
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
 def main():
     from oracle import refbinding as ref
     case = reference_case()
@@ -84,6 +101,24 @@ def main():
         out[f"lc_b_{l}"] = np.stack([it["b"] for it in its])
         out[f"lc_wp_{l}"] = np.array([it["weighted_pose"] for it in its], np.float32)
         out[f"lc_pose_{l}"] = np.stack([it["pose_after"] for it in its])
+    # depthMap::updateDepthImage / buildInvVarDepth / mapDepthArr2Mat / calculate_no_of_Seeds on seeded
+    # hypotheses (inputs are regenerated from the seed by the tests; the reference's outputs are stored as SHA-256 digests)
+    valid, idep, var = hypotheses_case(k["height"], k["width"])
+    r = ref.update_depth_image(kf["image"], valid, idep, var)
+    out["hyp_occupancy"] = np.array([r["occupancy"]], np.float32)
+    out["hyp_valid_sha"] = np.array(digest(r["valid_out"]))
+    out["hyp_depth_sha"] = np.array([digest(a) for a in r["depth"]])
+    out["hyp_var_sha"] = np.array([digest(a) for a in r["var"]])
+    out["hyp_selected"] = np.array([int((a > 0).sum()) for a in r["depth"]], np.int32)
+    # calculateImageHistogram / compareImageHistogram / calculateRotationStats on the fixture's frames
+    n = len(case["frames"])
+    out["gate_hist"] = np.stack([ref.gating(case["frames"][i], case["frames"][i], case["gt"][i], case["gt"][i])["hist_a"] for i in range(n)])
+    kl = np.zeros((n, n)); rms = np.zeros((n, n), np.float32); ang = np.zeros((n, n), np.float32)
+    for i in range(n):
+        for j in range(n):
+            gt = ref.gating(case["frames"][i], case["frames"][j], case["gt"][i], case["gt"][j])
+            kl[i, j], rms[i, j], ang[i, j] = gt["kl"], gt["rms_error"], gt["relative_view_angle"]
+    out["gate_kl"], out["gate_rms"], out["gate_angle"] = kl, rms, ang
     path = os.path.join(HERE, "reference_track_480x270.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")

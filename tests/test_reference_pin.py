@@ -125,6 +125,33 @@ def test_oracle_loop_closure_flow_is_bit_identical_to_the_reference(oracle_mod, 
         assert np.array_equal(np.stack([it["pose_after"] for it in its]), g[f"lc_pose_{l}"]), l
 
 
+def test_oracle_depth_pyramids_and_gating_are_bit_identical_to_the_reference(oracle_mod, fx):
+    """SURVEY 8f rows 2 and 3 against the reference's own src/DepthPropagation.cpp (updateDepthImage :1254-1315, buildInvVarDepth
+    :1637-1719, mapDepthArr2Mat, calculate_no_of_Seeds :1804-1830) and src/GlobalOptimize.cpp (calculateImageHistogram :40-100,
+    compareImageHistogram :116-122, calculateRotationStats :419-452).  The reference's depth / variance pyramids are stored as
+    SHA-256 digests: equal digests = bit-identical arrays (incl. inf depths from zero inverse depths and the NaN view angle of
+    identical poses)."""
+    import sys
+    sys.path.insert(0, GOLD)
+    from make_reference_golden import digest, hypotheses_case
+    g = fx
+    valid, idep, var = hypotheses_case(int(g["height"][0]), int(g["width"][0]))
+    o = oracle_mod.update_depth_image(valid, idep, var)
+    assert np.float32(o["occupancy"]) == g["hyp_occupancy"][0]
+    assert digest(o["valid_out"]) == str(g["hyp_valid_sha"])
+    assert [digest(a) for a in o["depth"]] == list(g["hyp_depth_sha"])
+    assert [digest(a) for a in o["var"]] == list(g["hyp_var_sha"])
+    n = len(g["frames"])
+    hists = [oracle_mod.image_histogram(g["frames"][i]) for i in range(n)]
+    assert np.array_equal(np.stack(hists), g["gate_hist"])
+    for i in range(n):
+        for j in range(n):
+            assert oracle_mod.hist_kl_div(hists[i], hists[j]) == g["gate_kl"][i, j]
+            rms, ang = oracle_mod.rotation_stats(g["gt"][i], g["gt"][j])
+            assert np.float32(rms) == g["gate_rms"][i, j]
+            assert np.array_equal(np.float32(ang), g["gate_angle"][i, j], equal_nan=True)
+
+
 # ---- live: the library itself (this container) ----------------------------------------------------------------------------
 @live
 def test_fixture_is_what_the_reference_produces(fx):
