@@ -134,3 +134,31 @@ def test_shim_tracks_like_the_reference_driver(tmp_path, oracle_mod):
     opose, otr = oracle_mod.track_lc(ocfg, kf["image"], frames[n - 1], kf["depth"], wf, init)
     got = np.array([l for l in lines if l[0] == "lcpose"][0][1:7], np.float64)
     assert np.abs(got - opose).max() < 1e-4
+
+
+@pytest.mark.gpu
+def test_shim_against_the_reference_driver_fixture(tmp_path):
+    """The drop-in C++ surface (our frame / depthMap / GetImagePoseEstimate on the GPU) next to the REFERENCE'S OWN driver on
+    the same inputs: tests/golden/reference_track_480x270.npz holds what the reference's GetImagePoseEstimate returned and the
+    poseWrtWorld it left behind (src/ImageFunc.cpp:305-307) for a keyframe at the origin and a t-1 frame at the origin."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "reference_track_480x270.npz"))
+    exe = build_shim()
+    w, h = int(g["width"][0]), int(g["height"][0])
+    blob = tmp_path / "ref_case.bin"
+    with open(blob, "wb") as f:
+        f.write(struct.pack("<iii4f", w, h, 1, *(float(v) for v in g["intr"])))
+        f.write(g["kf_image"].tobytes())
+        for l in range(4):
+            f.write(np.ascontiguousarray(g[f"depth{l}"], np.float32).tobytes())
+        for l in range(4):
+            f.write(np.ascontiguousarray(g[f"var{l}"], np.float32).tobytes())
+        f.write(g["frames"][0].tobytes())
+    out = subprocess.check_output([exe, str(blob)], text=True)
+    lines = [l.split() for l in out.strip().splitlines()]
+    pose = np.array([l for l in lines if l[0] == "pose"][0][2:8], np.float64)
+    world = np.array([l for l in lines if l[0] == "world"][0][2:8], np.float64)
+    post = [l for l in lines if l[0] == "post"][0]
+    assert np.abs(pose - g["p0_driver_pose"]).max() < 2e-6
+    assert np.abs(world - g["p0_driver_pose_wrt_world"]).max() < 2e-6
+    assert post[2:5] == ["0", "0", str(int(g["p0_n_selected"][0]))]          # both frames back at level 0, level-0 mask count
+    assert [l for l in lines if l[0] == "pyr"][0][1:] == ["240", "135", "60", "34"]      # pyrDown dims at 480x270: (h+1)/2 rows
