@@ -275,6 +275,13 @@ def main():
 
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # The only collective is the gather of 256-byte result records (1.2 MB per rank and step): latency-bound, and it runs
+        # WHILE the tracking kernel of the next step owns the SMs.  NCCL's defaults (many channels, Simple protocol) park a CTA on
+        # many SMs while ranks wait for each other, and every such SM loses one of its two resident tracking CTAs (measured at
+        # N = 2: tracking kernel 14.1 -> 16.9 ms, 92 % scaling).  One channel + the low-latency protocol: 14.1 ms, 98-99 %.
+        os.environ.setdefault("NCCL_MAX_NCHANNELS", "1")
+        os.environ.setdefault("NCCL_MIN_NCHANNELS", "1")
+        os.environ.setdefault("NCCL_PROTO", "LL")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     k = synth.intrinsics(W, H)
     cfg = capi.default_config(W, H, fx=float(k["fx"]), fy=float(k["fy"]), cx=float(k["cx"]), cy=float(k["cy"]),
