@@ -367,4 +367,40 @@ int ellc_ref_gating(const uint8_t* gray_a, const uint8_t* gray_b, const float po
     return 0;
 }
 
+// The matrix-form tracker of src/Pyramid.cpp.  The reference constructs it at every level but never iterates it
+// (performIterationSteps is not called from src/ImageFunc.cpp:192-226); here it is driven the way its own comments describe:
+// performPrecomputation() at the given pose (:700-711), then `iters` x performIterationSteps() (:714-726).
+// Outputs: n = selected pixels; weights / residual (1 x n, selection order) and last_err = sum w r^2 / n at the INPUT pose (:682);
+// hessian_inv of the first iteration; pose after each iteration; error ratios returned by performIterationSteps.
+int ellc_ref_pyramid_run(const uint8_t* kf_gray, const uint8_t* cur_gray, const float* const* depth, const float* const* var, int level,
+                         const float pose_in[6], int iters, int* n_sel, float* weights, float* residual, float* last_err,
+                         float hessian_inv[36], float* poses_after, float* ratios) {
+    init_once();
+    frame* kf = make_frame(kf_gray);
+    frame* cur = make_frame(cur_gray);
+    DepthHolder dh;
+    set_keyframe_depth(kf, dh, depth, var);
+    kf->updationOnPyrChange(level);
+    cur->updationOnPyrChange(level, false);
+    float pose[6];
+    for (int i = 0; i < 6; ++i) pose[i] = pose_in[i];
+    Pyramid wp(kf, cur, pose, dh.dm);
+    wp.putPreviousPose(cur);
+    wp.pose = pose;
+    wp.performPrecomputation();
+    const int n = kf->no_nonZeroDepthPts;
+    *n_sel = n;
+    *last_err = wp.lastErr;
+    for (int i = 0; i < n; ++i) { weights[i] = wp.weights.ptr<float>(0)[i]; residual[i] = wp.residual.ptr<float>(0)[i]; }
+    for (int it = 0; it < iters; ++it) {
+        ratios[it] = wp.performIterationSteps();
+        if (it == 0)
+            for (int i = 0; i < 6; ++i)
+                for (int j = 0; j < 6; ++j) hessian_inv[i * 6 + j] = wp.hessianInv.at<float>(i, j);
+        for (int i = 0; i < 6; ++i) poses_after[it * 6 + i] = pose[i];
+    }
+    delete kf; delete cur;
+    return 0;
+}
+
 }  // extern "C"

@@ -204,3 +204,18 @@ def gating(image_a, image_b, pose_a, pose_b):
     lib().ellc_ref_gating(_p(np.ascontiguousarray(image_a, np.uint8)), _p(np.ascontiguousarray(image_b, np.uint8)), _p(_f6(pose_a)),
                           _p(_f6(pose_b)), _p(ha), _p(hb), C.byref(kl), C.byref(rms), C.byref(ang))
     return dict(hist_a=ha, hist_b=hb, kl=kl.value, rms_error=rms.value, relative_view_angle=ang.value)
+
+
+def pyramid_run(kf_image, cur_image, depth_pyr, var_pyr, level, pose, iters=1):
+    """src/Pyramid.cpp driven as its comments describe: performPrecomputation at `pose`, then `iters` performIterationSteps."""
+    dm = dims()
+    kf_image = np.ascontiguousarray(kf_image, np.uint8); cur_image = np.ascontiguousarray(cur_image, np.uint8)
+    d, dp = _pyr_ptrs(depth_pyr); v, vp = _pyr_ptrs(var_pyr)
+    cap = (dm["height"] >> level) * (dm["width"] >> level)
+    w = np.zeros(cap, np.float32); r = np.zeros(cap, np.float32)
+    n = C.c_int(); le = C.c_float()
+    hinv = np.zeros(36, np.float32); poses = np.zeros((iters, 6), np.float32); ratios = np.zeros(iters, np.float32)
+    lib().ellc_ref_pyramid_run(_p(kf_image), _p(cur_image), dp, vp, level, _p(_f6(pose)), iters, C.byref(n), _p(w), _p(r), C.byref(le),
+                               _p(hinv), _p(poses), _p(ratios))
+    return dict(n=n.value, weights=w[:n.value].copy(), residual=r[:n.value].copy(), last_err=le.value, hessian_inv=hinv.reshape(6, 6),
+                poses_after=poses, ratios=ratios)

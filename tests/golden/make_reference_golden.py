@@ -119,6 +119,17 @@ def main():
             gt = ref.gating(case["frames"][i], case["frames"][j], case["gt"][i], case["gt"][j])
             kl[i, j], rms[i, j], ang[i, j] = gt["kl"], gt["rms_error"], gt["relative_view_angle"]
     out["gate_kl"], out["gate_rms"], out["gate_angle"] = kl, rms, ang
+    # the matrix-form src/Pyramid.cpp driven as its comments describe (performPrecomputation at a pose, then
+    # performIterationSteps): per-pixel weights digest, sum w r^2 / n (:682), hessianInv and the pose after the first update
+    pyr_cases = [(0, 2, np.zeros(6, np.float32)), (1, 1, (case["gt"][1] * 0.5).astype(np.float32)), (2, 3, np.zeros(6, np.float32))]
+    out["pyr_frame_level"] = np.array([(f, l) for f, l, _ in pyr_cases], np.int32)
+    out["pyr_pose_in"] = np.stack([p for _, _, p in pyr_cases])
+    rr = [ref.pyramid_run(kf["image"], case["frames"][f], kf["depth"], kf["var"], l, p, iters=2) for f, l, p in pyr_cases]
+    out["pyr_n"] = np.array([r["n"] for r in rr], np.int32)
+    out["pyr_last_err"] = np.array([r["last_err"] for r in rr], np.float32)
+    out["pyr_weights_sha"] = np.array([digest(r["weights"]) for r in rr])
+    out["pyr_hessian_inv"] = np.stack([r["hessian_inv"] for r in rr])
+    out["pyr_poses_after"] = np.stack([r["poses_after"] for r in rr])
     path = os.path.join(HERE, "reference_track_480x270.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")

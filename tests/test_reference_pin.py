@@ -152,6 +152,32 @@ def test_oracle_depth_pyramids_and_gating_are_bit_identical_to_the_reference(ora
             assert np.array_equal(np.float32(ang), g["gate_angle"][i, j], equal_nan=True)
 
 
+def test_oracle_pyramid_cpp_variant_is_bit_identical_to_the_reference(oracle_mod, fx):
+    """the oracle's `jacobian_at_warped` variant against the reference's matrix-form src/Pyramid.cpp
+    (calculateSteepestDescent :43-148 at the warped pixel and Z', calResidualAndWeights :558-694 with the weight of an
+    out-of-bounds pixel not zeroed, calculateHessianInv :153-207, updatePose :528-553): per-pixel weights, hessianInv and the
+    updated pose bit-identical; sum w r^2 / n within the float rounding of the reference's own division."""
+    import sys
+    sys.path.insert(0, GOLD)
+    from make_reference_golden import digest
+    g = fx
+    ocfg = _ocfg(oracle_mod, g, jacobian_at_warped=1)
+    depth, var = _depth(g)
+    kpyr = oracle_mod.image_pyramid(g["kf_image"])
+    for c, (fi, level) in enumerate(g["pyr_frame_level"]):
+        pose = g["pyr_pose_in"][c]
+        cpyr = oracle_mod.image_pyramid(g["frames"][fi])
+        o = oracle_mod.gn_evaluate(ocfg, int(level), kpyr[level], cpyr[level], depth[level], var[level], pose, want_weights=True)
+        sel = depth[level] > 0
+        assert int(sel.sum()) == int(g["pyr_n"][c])
+        assert digest(o["weights"][sel]) == str(g["pyr_weights_sha"][c]), c
+        assert abs(o["res_sum_f32"] / g["pyr_n"][c] - g["pyr_last_err"][c]) <= 2e-6 * g["pyr_last_err"][c], c
+        Hinv, ok = oracle_mod.invert6(o["H"])
+        assert ok and np.array_equal(Hinv, g["pyr_hessian_inv"][c]), c
+        pose_after, _, _ = oracle_mod.update_pose(ocfg, Hinv, o["b"], pose)
+        assert np.array_equal(pose_after, g["pyr_poses_after"][c][0]), c
+
+
 # ---- live: the library itself (this container) ----------------------------------------------------------------------------
 @live
 def test_fixture_is_what_the_reference_produces(fx):
