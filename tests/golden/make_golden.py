@@ -110,9 +110,36 @@ def main_gating():
     print("wrote gating_vectors.npz")
 
 
+def main_matops():
+    """Semantics of the cv::Mat expressions the tracker relies on, recorded from cv2 (own file; older fixtures stay byte-identical):
+      * gemm on CV_32F (hessian = weightedSteepestDescent * steepestDescent.t(), src/PixelWisePyramid.cpp:938; the 6x1 * 1x6
+        products :373; hessianInv * sd_param.t() :466): double accumulator, rounded to float once;
+      * Mat / scalar (frame::finaliseWeights, src/Frame.cpp:688) is MatOp_AddEx with alpha = 1./s evaluated by convertTo, whose
+        CV_32F kernel multiplies by (float)alpha -- observed here through cv2.normalize(NORM_MINMAX), which calls
+        src.convertTo(dst, CV_32F, scale, shift) with scale = alpha when the input spans exactly [0, 1]."""
+    import cv2
+    rng = np.random.default_rng(20261019)
+    out = {}
+    for tag, n in (("small", 7), ("large", 4000)):
+        A = (rng.standard_normal((6, n)) * np.array([[800, 800, 800, 90, 90, 90]]).T).astype(np.float32)
+        B = rng.standard_normal((n, 6)).astype(np.float32)
+        out[f"gemm_A_{tag}"], out[f"gemm_B_{tag}"] = A, B
+        out[f"gemm_C_{tag}"] = cv2.gemm(A, B, 1.0, None, 0.0)
+    x = rng.uniform(0, 1, (1, 3000)).astype(np.float32)
+    x[0, 0], x[0, 1] = 0.0, 1.0
+    out["scale_x"] = x
+    for n in (3, 5, 6, 7, 8):
+        out[f"scale_y_{n}"] = cv2.normalize(x, None, alpha=1.0 / n, beta=0.0, norm_type=cv2.NORM_MINMAX, dtype=cv2.CV_32F)
+    np.savez_compressed(os.path.join(HERE, "matop_vectors.npz"), **out)
+    print("wrote matop_vectors.npz")
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "gating":
         main_gating()
+    elif len(sys.argv) > 1 and sys.argv[1] == "matops":
+        main_matops()
     else:
         main()
         main_gating()
+        main_matops()

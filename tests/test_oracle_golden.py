@@ -138,3 +138,23 @@ def test_gating_histogram_and_kl_vs_cv2(oracle_mod):
             else:
                 assert abs(ang - g["view_angle_deg"][i, j]) <= 2e-2 + 1e-4 * g["view_angle_deg"][i, j]  # acos of a float dot near 1
 
+
+
+def test_cv_mat_expression_semantics_vs_cv2(oracle_mod):
+    """tests/golden/matop_vectors.npz (recorded from cv2 by make_golden.py matops): what `A * B` and `M / scalar` mean for CV_32F.
+    gemm accumulates in double and rounds once (the hessian of the constant-weight tracker, src/PixelWisePyramid.cpp:938);
+    `weight_pyramid / numWeightsAdded` (src/Frame.cpp:688) multiplies by the float reciprocal -- for 3, 5, 6, 7 saved weight
+    images that is NOT the quotient in about a third of the pixels, and the oracle / device / host shim follow the product."""
+    g = np.load(os.path.join(GOLD, "matop_vectors.npz"))
+    for tag in ("small", "large"):
+        A, B = g[f"gemm_A_{tag}"], g[f"gemm_B_{tag}"]
+        assert np.array_equal((A.astype(np.float64) @ B.astype(np.float64)).astype(np.float32), g[f"gemm_C_{tag}"])
+    x = g["scale_x"]
+    differs = 0
+    for n in (3, 5, 6, 7, 8):
+        y = g[f"scale_y_{n}"]
+        got = oracle_mod.finalise_weights([x.copy() for _ in range(4)], [n] * 4)
+        for l in range(4):
+            assert np.array_equal(got[l], y)
+        differs += int((y != x / np.float32(n)).sum())
+    assert differs > 1000
