@@ -357,7 +357,7 @@ static int ensure_lc_pools(ellc_handle* h) {
     const int64_t nf = h->cfg.max_frames, nk = h->cfg.max_keyframes;
     CU_TRY(h, cudaMalloc(&h->fr_weight, (size_t)(nf * win) * sizeof(float)));
     CU_TRY(h, cudaMalloc(&h->kf_lc, (size_t)(nk * win + kRecTail) * sizeof(LcRec)));
-    CU_TRY(h, cudaMalloc(&h->kf_lcH, (size_t)nk * kLevels * 36 * sizeof(float)));
+    CU_TRY(h, cudaMalloc(&h->kf_lcH, (size_t)nk * kLevels * kLcHStride * sizeof(float)));
     CU_TRY(h, cudaMalloc(&h->kf_weight, (size_t)(nk * win) * sizeof(float)));
     CU_TRY(h, cudaMemsetAsync(h->fr_weight, 0, (size_t)(nf * win) * sizeof(float), h->stream));
     CU_TRY(h, cudaMemsetAsync(h->kf_weight, 0, (size_t)(nk * win) * sizeof(float), h->stream));     // Mat::zeros, src/Frame.cpp:114-117

@@ -9,6 +9,7 @@
 namespace ellc {
 
 constexpr int kLevels = ELLC_LEVELS;
+constexpr int kLcHStride = 80;              // floats per (keyframe, level) record of the loop-closure hessian: H, H^-1, ok, pad
 
 // One selected keyframe pixel (mask != 0, src/Frame.cpp:298), produced once per keyframe level by the selection
 // kernels and streamed by every GN iteration as two coalesced loads (16 B + 4 B, structure of arrays).
@@ -108,7 +109,7 @@ struct TrackParams {
     float* weight_out;         // optional display_weightimg of the evaluated level (cols x rows), evaluate-only mode
     float* frw_pool;           // per frame slot: display_weightimg of every level (win layout) for ELLC_PAIR_SAVE_WEIGHTS pairs
     const LcRec* lc_pool;      // loop-closure records, per keyframe slot (rec_slot_stride)
-    const float* lc_H;         // [kf_slot][kLevels][36] precomputed hessian (src/PixelWisePyramid.cpp:938)
+    const float* lc_H;         // [kf_slot][kLevels][kLcHStride]: hessian (36, src/PixelWisePyramid.cpp:938), hessianInv (36, :939), ok (1)
     uint32_t zero_mask;        // always 0: an opaque zero the pixel loop uses to build ordering dependences
 };
 

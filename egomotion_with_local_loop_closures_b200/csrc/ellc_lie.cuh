@@ -527,11 +527,9 @@ static __device__ __noinline__ float se3_exp_pade_warp(float p0, float p1, float
 // weighted_pose).  The 4x4 part runs lane-distributed: rt_pose_e is entry (lane & 15) of exp(hat(pose)) as computed for the
 // current iteration (rows 0..2 from Rt, row 3 exactly [0 0 0 1]), and *rt_new_e returns the same entry of exp(hat(new pose)) for
 // the next iteration (src/PixelWisePyramid.cpp:153-173), so only exp(delta) and exp(new pose) are evaluated.
-__device__ inline bool solve_update_warp(const float (&H)[36], const float (&b)[6], const float (&weight)[6], float rt_pose_e,
-                                         float (&pose)[6], float (&delta)[6], float* weighted_pose, float* rt_new_e, int lane) {
-    float col[6];
-    bool ok;
-    invert6_lu_warp(H, lane, col, &ok);
+// updatePose() given column (lane % 6) of hessianInv in col[0..5] (all zeros for a singular hessian)
+__device__ inline void update_from_inverse_warp(const float (&col)[6], const float (&b)[6], const float (&weight)[6], float rt_pose_e,
+                                                float (&pose)[6], float (&delta)[6], float* weighted_pose, float* rt_new_e, int lane) {
     // delta_i = -(sum_k Hinv[i][k] b[k]): lane k (< 6) holds Hinv[.][k]; products are exact in double, the sum runs k = 0..5
     const double bk = (double)b[lane % 6];
     ELLC_UNROLL
@@ -555,6 +553,13 @@ __device__ inline bool solve_update_warp(const float (&H)[36], const float (&b)[
     T[12] = T[13] = T[14] = 0.f; T[15] = 1.f;                  // not read by the logarithm
     m4_log_f(T, pose);
     *rt_new_e = se3_exp_pade_warp(pose[0], pose[1], pose[2], pose[3], pose[4], pose[5], e);
+}
+__device__ inline bool solve_update_warp(const float (&H)[36], const float (&b)[6], const float (&weight)[6], float rt_pose_e,
+                                         float (&pose)[6], float (&delta)[6], float* weighted_pose, float* rt_new_e, int lane) {
+    float col[6];
+    bool ok;
+    invert6_lu_warp(H, lane, col, &ok);
+    update_from_inverse_warp(col, b, weight, rt_pose_e, pose, delta, weighted_pose, rt_new_e, lane);
     return ok;
 }
 #endif  // __CUDACC__

@@ -9,6 +9,7 @@
 //
 // All kernels are batched over slots (blockIdx.z / blockIdx.y) so that a whole batch of frames costs 4 launches.
 #include "ellc_internal.h"
+#include "ellc_lie.cuh"
 
 namespace ellc {
 
@@ -434,10 +435,25 @@ lc_prepare_kernel(const SelGeo* __restrict__ geo_pool, const SelPix* __restrict_
         if (lane == 0) s_part[warp][i] = v;
     }
     __syncthreads();
+    __shared__ float s_H[36];
+    float* const rec = lc_H + ((int64_t)slot * kLevels + level) * kLcHStride;
     if (threadIdx.x < 36) {
         double t = s_part[0][threadIdx.x];
         for (int w = 1; w < 8; ++w) t += s_part[w][threadIdx.x];
-        lc_H[((int64_t)slot * kLevels + level) * 36 + threadIdx.x] = (float)t;
+        s_H[threadIdx.x] = (float)t;
+        rec[threadIdx.x] = (float)t;
+    }
+    __syncthreads();
+    // hessianInv = hessian.inv() is taken ONCE per level by the reference too (iter == 0, :939): store it with the hessian, so
+    // that an iteration of the loop-closure tracker starts at deltapose = -(hessianInv sd_param) without a 6x6 LU
+    if (threadIdx.x == 0) {
+        float H[36], Hinv[36];
+#pragma unroll
+        for (int i = 0; i < 36; ++i) H[i] = s_H[i];
+        const bool ok = invert6_lu_f(H, Hinv);
+#pragma unroll
+        for (int i = 0; i < 36; ++i) rec[36 + i] = Hinv[i];
+        rec[72] = ok ? 1.f : 0.f;
     }
 }
 
