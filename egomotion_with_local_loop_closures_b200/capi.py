@@ -70,7 +70,8 @@ SYMBOLS = ["ellc_default_config", "ellc_create", "ellc_destroy", "ellc_last_erro
            "ellc_read_keyframe_level", "ellc_level_dims", "ellc_concat_relative", "ellc_concat_origin",
            "ellc_se3_exp", "ellc_launch_count", "ellc_reset_launch_count", "ellc_stream", "ellc_stream_of", "ellc_selftest_division", "ellc_reset_keyframe_weights", "ellc_accumulate_weights",
            "ellc_finalise_weights", "ellc_upload_keyframe_weights", "ellc_read_keyframe_weights", "ellc_read_frame_weights",
-           "ellc_prepare_keyframes_lc", "ellc_frame_histograms", "ellc_lc_gate", "ellc_upload_keyframe_hypotheses", "ellc_read_keyframe_occupancy", "ellc_read_keyframe_depth", "ellc_last_track_kernel_ms"]
+           "ellc_prepare_keyframes_lc", "ellc_frame_histograms", "ellc_lc_gate", "ellc_upload_keyframe_hypotheses", "ellc_read_keyframe_occupancy", "ellc_read_keyframe_depth", "ellc_last_track_kernel_ms",
+           "ellc_prepare_async", "ellc_batch_kernel_ms"]
 
 _lib = None
 
@@ -130,6 +131,9 @@ def lib():
         L.ellc_stream_of.argtypes = [C.c_void_p, C.c_int32]
         L.ellc_last_track_kernel_ms.restype = C.c_float
         L.ellc_last_track_kernel_ms.argtypes = [C.c_void_p]
+        L.ellc_batch_kernel_ms.restype = C.c_float
+        L.ellc_batch_kernel_ms.argtypes = [C.c_void_p, C.c_int32]
+        L.ellc_prepare_async.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
         _lib = L
     return _lib
 
@@ -406,3 +410,11 @@ class Tracker:
 
     def last_track_kernel_ms(self):
         return lib().ellc_last_track_kernel_ms(self._h)
+
+    def batch_kernel_ms(self, batches_ago=0):
+        return lib().ellc_batch_kernel_ms(self._h, int(batches_ago))
+
+    def prepare_async(self, frame_slots, kf_slots):
+        """Preparation of these slots on the low-priority preparation stream (overlaps the batch that is tracking now)."""
+        f = np.ascontiguousarray(frame_slots, np.int32); k = np.ascontiguousarray(kf_slots, np.int32)
+        self._chk(lib().ellc_prepare_async(self._h, len(f), _p(f), len(k), _p(k)))

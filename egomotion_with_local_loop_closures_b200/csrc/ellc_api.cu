@@ -32,8 +32,11 @@ struct ellc_handle {
     cudaStream_t stream;                               // compute: prepare kernels, track kernel, small staging copies
     cudaStream_t copy_stream;                          // H2D uploads of images / depth / variance (overlap with compute)
     cudaStream_t d2h_stream;                           // result downloads of finished batches
-    cudaEvent_t ev0, ev1;
+    cudaEvent_t ev0r[4], ev1r[4];                      // track-kernel timing events of the last four batches (index: sequence & 3)
     cudaEvent_t up_ev;                                 // re-recorded after every upload on copy_stream
+    cudaStream_t prep_stream;                          // preparation of freshly uploaded slots (overlaps the previous batch's kernels)
+    cudaEvent_t prep_ev;                               // recorded after every such preparation; the compute stream waits for it
+    int* d_slots_p;                                    // slot lists of the preparation stream (2 x slots_cap)
     bool uploads_pending;
     cudaEvent_t batch_ev[4];                           // completion of the last 4 track batches (ring by sequence number)
     long long batch_seq, batch_done_seq;               // last enqueued / last known-complete batch
@@ -136,16 +139,18 @@ int ellc_destroy(ellc_handle* h) {
     cudaFree(h->kf_mask); cudaFree(h->kf_geo); cudaFree(h->kf_pix); cudaFree(h->kf_ikf);
     cudaFree(h->d_hyp); cudaFree(h->d_nvalid); cudaFree(h->fr_hist);
     cudaFree(h->fr_weight); cudaFree(h->kf_weight); cudaFree(h->kf_lc); cudaFree(h->kf_lcH); cudaFree(h->kf_count); cudaFree(h->kf_rowcount); cudaFree(h->kf_rowoff);
-    cudaFree(h->d_slots); cudaFree(h->d_pairs); cudaFree(h->d_results2[0]); cudaFree(h->d_results2[1]); cudaFree(h->d_order); cudaFree(h->d_trace); cudaFree(h->d_small);
+    cudaFree(h->d_slots); cudaFree(h->d_slots_p); cudaFree(h->d_pairs); cudaFree(h->d_results2[0]); cudaFree(h->d_results2[1]); cudaFree(h->d_order); cudaFree(h->d_trace); cudaFree(h->d_small);
     cudaFree(h->d_weight);
     if (h->h_pin) cudaFreeHost(h->h_pin);
     if (h->ev_valid) {
-        cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->up_ev);
+        for (int i = 0; i < 4; ++i) { cudaEventDestroy(h->ev0r[i]); cudaEventDestroy(h->ev1r[i]); }
+        cudaEventDestroy(h->up_ev); cudaEventDestroy(h->prep_ev);
         for (int i = 0; i < 4; ++i) cudaEventDestroy(h->batch_ev[i]);
     }
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
+    if (h->prep_stream) cudaStreamDestroy(h->prep_stream);
     delete h;
     return ELLC_OK;
 }
@@ -191,12 +196,17 @@ int ellc_create(const ellc_config* cfg, ellc_handle** out) {
         }                                                                                            \
     } while (0)
     CR_TRY(cudaSetDevice(cfg->device));
-    CR_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    // The tracking kernels get the highest CTA-scheduling priority, the preparation stream the lowest: preparation of the next
+    // batch runs in the SM time the tracking kernel of the current one leaves over (mostly its last wave) instead of slowing it down.
+    int prio_least = 0, prio_greatest = 0;
+    CR_TRY(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+    CR_TRY(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_greatest));
     CR_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     CR_TRY(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
-    CR_TRY(cudaEventCreate(&h->ev0));
-    CR_TRY(cudaEventCreate(&h->ev1));
+    CR_TRY(cudaStreamCreateWithPriority(&h->prep_stream, cudaStreamNonBlocking, prio_least));
+    for (int i = 0; i < 4; ++i) { CR_TRY(cudaEventCreate(&h->ev0r[i])); CR_TRY(cudaEventCreate(&h->ev1r[i])); }
     CR_TRY(cudaEventCreateWithFlags(&h->up_ev, cudaEventDisableTiming));
+    CR_TRY(cudaEventCreateWithFlags(&h->prep_ev, cudaEventDisableTiming));
     for (int i = 0; i < 4; ++i) CR_TRY(cudaEventCreateWithFlags(&h->batch_ev[i], cudaEventDisableTiming));
     h->ev_valid = true;
     h->fr_reader.assign(cfg->max_frames, 0);
@@ -224,6 +234,7 @@ int ellc_create(const ellc_config* cfg, ellc_handle** out) {
     CR_TRY(cudaMalloc(&h->kf_rowoff, nk * h->rows_total * sizeof(int)));
     h->slots_cap = (int)(nf > nk ? nf : nk);
     CR_TRY(cudaMalloc(&h->d_slots, 2 * h->slots_cap * sizeof(int)));
+    CR_TRY(cudaMalloc(&h->d_slots_p, 2 * h->slots_cap * sizeof(int)));
     CR_TRY(cudaMalloc(&h->d_small, 128 * sizeof(float)));
     h->pin_cap = 8 << 20;
     CR_TRY(cudaHostAlloc(&h->h_pin, h->pin_cap, cudaHostAllocMapped));
@@ -240,13 +251,14 @@ int ellc_create(const ellc_config* cfg, ellc_handle** out) {
 
 // ---- internal helpers ------------------------------------------------------------------------------------------------
 // Copy a small host payload to the device through the pinned arena (no implicit host/device serialisation).
-static int stage_h2d(ellc_handle* h, void* dst, const void* src, size_t bytes) {
+static int stage_h2d_on(ellc_handle* h, cudaStream_t st, void* dst, const void* src, size_t bytes) {
     if (bytes > h->pin_cap / 2) {           // large payload: plain (staged) async copy
-        CU_TRY(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
+        CU_TRY(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
         return ELLC_OK;
     }
     const size_t aligned = (bytes + 255) & ~(size_t)255;
     if (h->pin_used + aligned > h->pin_cap) {
+        CU_TRY(h, cudaStreamSynchronize(h->prep_stream));
         CU_TRY(h, cudaStreamSynchronize(h->stream));
         h->pin_used = 0;
     }
@@ -254,10 +266,11 @@ static int stage_h2d(ellc_handle* h, void* dst, const void* src, size_t bytes) {
     std::memcpy(p, src, bytes);
     h->pin_used += aligned;
     // pulled by the SMs, not the copy engine: see pull_host_words_kernel
-    h->launches += launch_pull_host(h->stream, dst, (char*)h->d_pin + ((char*)p - (char*)h->h_pin), bytes);
+    h->launches += launch_pull_host(st, dst, (char*)h->d_pin + ((char*)p - (char*)h->h_pin), bytes);
     CU_TRY(h, cudaGetLastError());
     return ELLC_OK;
 }
+static int stage_h2d(ellc_handle* h, void* dst, const void* src, size_t bytes) { return stage_h2d_on(h, h->stream, dst, src, bytes); }
 
 
 // An upload overwrites a slot on copy_stream.  It must not pass a track batch (compute stream) that still reads the slot:
@@ -299,25 +312,29 @@ static int ensure_pairs_cap(ellc_handle* h, int n, bool want_trace) {
     return ELLC_OK;
 }
 
-static int prepare_frames_impl(ellc_handle* h, int n, const int* slots) {
+// side = true: on the preparation stream with its own slot lists (freshly uploaded slots, see flush_dirty)
+static int prepare_frames_impl(ellc_handle* h, int n, const int* slots, bool side = false) {
     if (n <= 0) return ELLC_OK;
-    int rc = stage_h2d(h, h->d_slots, slots, (size_t)n * sizeof(int));
+    cudaStream_t st = side ? h->prep_stream : h->stream;
+    int* d_slots = side ? h->d_slots_p : h->d_slots;
+    int rc = stage_h2d_on(h, st, d_slots, slots, (size_t)n * sizeof(int));
     if (rc) return rc;
-    h->launches += launch_pyramid(h->stream, h->fr_img, h->geo.img_off[kLevels], h->d_slots, n, h->geo);
-    h->launches += launch_pack_tex(h->stream, h->fr_img, h->geo.img_off[kLevels], h->fr_tex, h->geo.win_off[kLevels] + kTexPad,
-                                   h->d_slots, n, h->geo);
+    h->launches += launch_pyramid(st, h->fr_img, h->geo.img_off[kLevels], d_slots, n, h->geo);
+    h->launches += launch_pack_tex(st, h->fr_img, h->geo.img_off[kLevels], h->fr_tex, h->geo.win_off[kLevels] + kTexPad,
+                                   d_slots, n, h->geo);
     CU_TRY(h, cudaGetLastError());
     for (int i = 0; i < n; ++i) h->fr_state[slots[i]] = 2;
     return ELLC_OK;
 }
 
-static int prepare_keyframes_impl(ellc_handle* h, int n, const int* slots) {
+static int prepare_keyframes_impl(ellc_handle* h, int n, const int* slots, bool side = false) {
     if (n <= 0) return ELLC_OK;
-    int* d_slots = h->d_slots + h->slots_cap;
-    int rc = stage_h2d(h, d_slots, slots, (size_t)n * sizeof(int));
+    cudaStream_t st = side ? h->prep_stream : h->stream;
+    int* d_slots = (side ? h->d_slots_p : h->d_slots) + h->slots_cap;
+    int rc = stage_h2d_on(h, st, d_slots, slots, (size_t)n * sizeof(int));
     if (rc) return rc;
-    h->launches += launch_pyramid(h->stream, h->kf_img, h->geo.img_off[kLevels], d_slots, n, h->geo);
-    h->launches += launch_select(h->stream, h->kf_depth, h->kf_var, h->geo.win_off[kLevels], h->kf_img,
+    h->launches += launch_pyramid(st, h->kf_img, h->geo.img_off[kLevels], d_slots, n, h->geo);
+    h->launches += launch_select(st, h->kf_depth, h->kf_var, h->geo.win_off[kLevels], h->kf_img,
                                  h->geo.img_off[kLevels], h->kf_mask, h->kf_rowcount, h->kf_rowoff, h->kf_count,
                                  h->kf_geo, h->kf_pix, h->kf_ikf, h->K, d_slots, n, h->geo);
     CU_TRY(h, cudaGetLastError());
@@ -325,26 +342,40 @@ static int prepare_keyframes_impl(ellc_handle* h, int n, const int* slots) {
     return ELLC_OK;
 }
 
+// Slots that were uploaded since the last call are prepared (pyramid, texels, selection) before anything reads them.  When the
+// uploads are still in flight on the copy stream -- a caller that uploads batch k+1 while batch k is tracking -- the
+// preparation goes to its own stream behind the uploads, so that it overlaps the tracking kernels of batch k (and fills the
+// SMs its last wave leaves idle) instead of queueing behind them; the compute stream then waits for the preparation only.
+// Safe: an upload already waits for every batch that reads its slot (guard_slot_write), and the preparation follows the upload.
 static int flush_dirty(ellc_handle* h) {
+    const bool side = h->uploads_pending && h->batch_seq > h->batch_done_seq;      // something may still be tracking
     if (h->uploads_pending) {                              // copy_stream is in order: the last upload's event covers them all
-        CU_TRY(h, cudaStreamWaitEvent(h->stream, h->up_ev, 0));
+        CU_TRY(h, cudaStreamWaitEvent(side ? h->prep_stream : h->stream, h->up_ev, 0));
         h->uploads_pending = false;
     }
+    bool launched = false;
     if (!h->fr_dirty.empty()) {
         std::vector<int> s;
         for (int v : h->fr_dirty) if (h->fr_state[v] == 1) { s.push_back(v); h->fr_state[v] = 3; }
         for (int v : s) h->fr_state[v] = 1;
         h->fr_dirty.clear();
-        int rc = prepare_frames_impl(h, (int)s.size(), s.data());
+        int rc = prepare_frames_impl(h, (int)s.size(), s.data(), side);
         if (rc) return rc;
+        launched = launched || !s.empty();
     }
     if (!h->kf_dirty.empty()) {
         std::vector<int> s;
         for (int v : h->kf_dirty) if (h->kf_state[v] == 1) { s.push_back(v); h->kf_state[v] = 3; }
         for (int v : s) h->kf_state[v] = 1;
         h->kf_dirty.clear();
-        int rc = prepare_keyframes_impl(h, (int)s.size(), s.data());
+        int rc = prepare_keyframes_impl(h, (int)s.size(), s.data(), side);
         if (rc) return rc;
+        launched = launched || !s.empty();
+    }
+    if (side) {                                            // also orders the compute stream behind the uploads themselves
+        (void)launched;
+        CU_TRY(h, cudaEventRecord(h->prep_ev, h->prep_stream));
+        CU_TRY(h, cudaStreamWaitEvent(h->stream, h->prep_ev, 0));
     }
     return ELLC_OK;
 }
@@ -478,7 +509,7 @@ static int track_launch(ellc_handle* h, int n, const ellc_pair* pairs, bool want
     TrackParams p;
     fill_params(h, p);
     p.pairs = h->d_pairs; p.order = h->d_order; p.results = h->d_results; p.trace = want_trace ? h->d_trace : nullptr; p.n_pairs = n;
-    CU_TRY(h, cudaEventRecord(h->ev0, h->stream));
+    CU_TRY(h, cudaEventRecord(h->ev0r[seq & 3], h->stream));
     p.n_pairs = n_fwd;
     const int cluster = pick_cluster(h, n_fwd);
     p.pairs_per_cta = pick_pairs_per_cta(h, n_fwd, cluster);
@@ -501,7 +532,7 @@ static int track_launch(ellc_handle* h, int n, const ellc_pair* pairs, bool want
         if (l < 0) { h->err = std::string("loop-closure track kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()); return ELLC_ERR_CUDA; }
         h->launches += l;
     }
-    CU_TRY(h, cudaEventRecord(h->ev1, h->stream));
+    CU_TRY(h, cudaEventRecord(h->ev1r[seq & 3], h->stream));
     CU_TRY(h, cudaEventRecord(h->batch_ev[seq & 3], h->stream));
     h->batch_seq = seq;
     for (int i = 0; i < n; ++i) { h->fr_reader[pairs[i].frame_slot] = seq; h->kf_reader[pairs[i].kf_slot] = seq; }
@@ -700,10 +731,45 @@ int ellc_prepare_keyframes(ellc_handle* h, int32_t n, const int32_t* slots) {
     return prepare_keyframes_impl(h, n, slots);
 }
 
+// Preparation on the preparation stream: it waits for pending uploads and for the last batch that READ any of these slots, not
+// for the batch that is tracking now -- so the pyramids / texels / selection lists of batch k+1 are built while batch k tracks.
+int ellc_prepare_async(ellc_handle* h, int32_t n_frames, const int32_t* frame_slots, int32_t n_keyframes, const int32_t* kf_slots) {
+    if (!h) return ELLC_ERR_INVALID;
+    if (n_frames < 0 || n_keyframes < 0 || (n_frames > 0 && !frame_slots) || (n_keyframes > 0 && !kf_slots) ||
+        n_frames > h->cfg.max_frames || n_keyframes > h->cfg.max_keyframes) { h->err = "bad slot lists"; return ELLC_ERR_INVALID; }
+    long long reader = 0;
+    for (int i = 0; i < n_frames; ++i) {
+        const int v = frame_slots[i];
+        if (v < 0 || v >= h->cfg.max_frames) { h->err = "frame slot out of range"; return ELLC_ERR_INVALID; }
+        if (h->fr_state[v] == 0) { h->err = "frame slot empty"; return ELLC_ERR_NOT_READY; }
+        reader = std::max(reader, h->fr_reader[v]);
+    }
+    for (int i = 0; i < n_keyframes; ++i) {
+        const int v = kf_slots[i];
+        if (v < 0 || v >= h->cfg.max_keyframes) { h->err = "keyframe slot out of range"; return ELLC_ERR_INVALID; }
+        if (h->kf_state[v] == 0) { h->err = "keyframe slot empty"; return ELLC_ERR_NOT_READY; }
+        reader = std::max(reader, h->kf_reader[v]);
+    }
+    CU_TRY(h, cudaSetDevice(h->cfg.device));
+    if (h->uploads_pending) CU_TRY(h, cudaStreamWaitEvent(h->prep_stream, h->up_ev, 0));   // (the flag stays: other consumers wait too)
+    if (reader > h->batch_done_seq) {
+        if (reader + 4 <= h->batch_seq) h->batch_done_seq = reader;                          // its ring entry was recycled => finished
+        else CU_TRY(h, cudaStreamWaitEvent(h->prep_stream, h->batch_ev[reader & 3], 0));
+    }
+    int rc = prepare_frames_impl(h, n_frames, frame_slots, true);
+    if (rc) return rc;
+    rc = prepare_keyframes_impl(h, n_keyframes, kf_slots, true);
+    if (rc) return rc;
+    CU_TRY(h, cudaEventRecord(h->prep_ev, h->prep_stream));
+    CU_TRY(h, cudaStreamWaitEvent(h->stream, h->prep_ev, 0));
+    return ELLC_OK;
+}
+
 int ellc_synchronize(ellc_handle* h) {
     if (!h) return ELLC_ERR_INVALID;
     CU_TRY(h, cudaSetDevice(h->cfg.device));
     CU_TRY(h, cudaStreamSynchronize(h->copy_stream));
+    CU_TRY(h, cudaStreamSynchronize(h->prep_stream));
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     CU_TRY(h, cudaStreamSynchronize(h->d2h_stream));
     h->batch_done_seq = h->batch_seq;
@@ -1027,8 +1093,18 @@ void* ellc_stream_of(ellc_handle* h, int32_t which) {
 float ellc_last_track_kernel_ms(ellc_handle* h) {
     if (!h || !h->ev_valid) return -1.f;
     float ms = -1.f;
-    if (cudaEventSynchronize(h->ev1) != cudaSuccess) return -1.f;
-    if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) != cudaSuccess) return -1.f;
+    const int r = (int)(h->batch_seq & 3);
+    if (cudaEventSynchronize(h->ev1r[r]) != cudaSuccess) return -1.f;
+    if (cudaEventElapsedTime(&ms, h->ev0r[r], h->ev1r[r]) != cudaSuccess) return -1.f;
+    return ms;
+}
+
+float ellc_batch_kernel_ms(ellc_handle* h, int32_t batches_ago) {
+    if (!h || !h->ev_valid || batches_ago < 0 || batches_ago > 3 || h->batch_seq - batches_ago < 1) return -1.f;
+    float ms = -1.f;
+    const int r = (int)((h->batch_seq - batches_ago) & 3);
+    if (cudaEventSynchronize(h->ev1r[r]) != cudaSuccess) return -1.f;
+    if (cudaEventElapsedTime(&ms, h->ev0r[r], h->ev1r[r]) != cudaSuccess) return -1.f;
     return ms;
 }
 

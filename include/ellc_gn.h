@@ -174,6 +174,11 @@ int ellc_keyframe_devptrs(ellc_handle* h, int32_t kf_slot, uint8_t** image, floa
                           int64_t level_offsets[ELLC_LEVELS + 1]);
 int ellc_prepare_frames(ellc_handle* h, int32_t n, const int32_t* frame_slots);      /* pyramid + gradients, batched */
 int ellc_prepare_keyframes(ellc_handle* h, int32_t n, const int32_t* kf_slots);      /* pyramid + mask/count/selection */
+/* (extension) The same two preparations on a separate low-priority stream that waits only for pending uploads and for the last
+ * batch that READ these slots -- not for the batch that is tracking now.  A caller that alternates between two sets of slots
+ * builds the pyramids / texels / selection lists of batch k+1 while batch k tracks.  The caller must not pass slots that the
+ * batch in flight (or any other pending call) uses. */
+int ellc_prepare_async(ellc_handle* h, int32_t n_frames, const int32_t* frame_slots, int32_t n_keyframes, const int32_t* kf_slots);
 
 /* ---- the hot path -------------------------------------------------------------------------------------------------
  * ellc_track_batch replaces n calls of GetImagePoseEstimate(prev_frame, current_frame, ...) (src/ImageFunc.cpp:49-315)
@@ -261,6 +266,8 @@ int ellc_selftest_division(ellc_handle* h, int64_t n, uint64_t seed, int64_t mis
 void*   ellc_stream_of(ellc_handle* h, int32_t which);
 /* device time of the track kernel(s) of the most recent ellc_track_batch* call, in milliseconds (CUDA events) */
 float   ellc_last_track_kernel_ms(ellc_handle* h);
+/* the same for an earlier batch: batches_ago = 0 is the most recent ellc_track_batch* call, up to 3 */
+float   ellc_batch_kernel_ms(ellc_handle* h, int32_t batches_ago);
 
 #ifdef __cplusplus
 }
