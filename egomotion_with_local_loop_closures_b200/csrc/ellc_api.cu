@@ -353,7 +353,6 @@ static int flush_dirty(ellc_handle* h) {
         CU_TRY(h, cudaStreamWaitEvent(side ? h->prep_stream : h->stream, h->up_ev, 0));
         h->uploads_pending = false;
     }
-    bool launched = false;
     if (!h->fr_dirty.empty()) {
         std::vector<int> s;
         for (int v : h->fr_dirty) if (h->fr_state[v] == 1) { s.push_back(v); h->fr_state[v] = 3; }
@@ -361,7 +360,6 @@ static int flush_dirty(ellc_handle* h) {
         h->fr_dirty.clear();
         int rc = prepare_frames_impl(h, (int)s.size(), s.data(), side);
         if (rc) return rc;
-        launched = launched || !s.empty();
     }
     if (!h->kf_dirty.empty()) {
         std::vector<int> s;
@@ -370,10 +368,8 @@ static int flush_dirty(ellc_handle* h) {
         h->kf_dirty.clear();
         int rc = prepare_keyframes_impl(h, (int)s.size(), s.data(), side);
         if (rc) return rc;
-        launched = launched || !s.empty();
     }
     if (side) {                                            // also orders the compute stream behind the uploads themselves
-        (void)launched;
         CU_TRY(h, cudaEventRecord(h->prep_ev, h->prep_stream));
         CU_TRY(h, cudaStreamWaitEvent(h->stream, h->prep_ev, 0));
     }
