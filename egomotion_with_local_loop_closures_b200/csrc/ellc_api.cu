@@ -51,7 +51,7 @@ struct ellc_handle {
     uint8_t* d_hyp; int* d_nvalid;
     std::vector<int> kf_nvalid;                        // -1: not uploaded from hypotheses / not fetched yet
     // loop-closure state, allocated on first use (ensure_lc_pools)
-    float* fr_weight; float* kf_weight; LcRec* kf_lc; float* kf_lcH;
+    float* fr_weight; float* kf_weight; LcRec* kf_lc; float* kf_lcH; float4* kf_lcf; uint32_t* kf_lcp;
     std::vector<int> kf_wcount;                        // numWeightsAdded[level] per keyframe slot
     std::vector<char> kf_lc_ready;                     // LcRec / hessian built for the slot's current contents
     int* kf_count; int* kf_rowcount; int* kf_rowoff;
@@ -138,7 +138,7 @@ int ellc_destroy(ellc_handle* h) {
     cudaFree(h->fr_img); cudaFree(h->fr_tex); cudaFree(h->kf_img); cudaFree(h->kf_depth); cudaFree(h->kf_var);
     cudaFree(h->kf_mask); cudaFree(h->kf_geo); cudaFree(h->kf_pix); cudaFree(h->kf_ikf);
     cudaFree(h->d_hyp); cudaFree(h->d_nvalid); cudaFree(h->fr_hist);
-    cudaFree(h->fr_weight); cudaFree(h->kf_weight); cudaFree(h->kf_lc); cudaFree(h->kf_lcH); cudaFree(h->kf_count); cudaFree(h->kf_rowcount); cudaFree(h->kf_rowoff);
+    cudaFree(h->fr_weight); cudaFree(h->kf_weight); cudaFree(h->kf_lc); cudaFree(h->kf_lcH); cudaFree(h->kf_lcf); cudaFree(h->kf_lcp); cudaFree(h->kf_count); cudaFree(h->kf_rowcount); cudaFree(h->kf_rowoff);
     cudaFree(h->d_slots); cudaFree(h->d_slots_p); cudaFree(h->d_pairs); cudaFree(h->d_results2[0]); cudaFree(h->d_results2[1]); cudaFree(h->d_order); cudaFree(h->d_trace); cudaFree(h->d_small);
     cudaFree(h->d_weight);
     if (h->h_pin) cudaFreeHost(h->h_pin);
@@ -389,6 +389,10 @@ static int ensure_lc_pools(ellc_handle* h) {
     CU_TRY(h, cudaMemsetAsync(h->fr_weight, 0, (size_t)(nf * win) * sizeof(float), h->stream));
     CU_TRY(h, cudaMemsetAsync(h->kf_weight, 0, (size_t)(nk * win) * sizeof(float), h->stream));     // Mat::zeros, src/Frame.cpp:114-117
     CU_TRY(h, cudaMemsetAsync(h->kf_lc, 0, (size_t)(nk * win + kRecTail) * sizeof(LcRec), h->stream));
+    CU_TRY(h, cudaMalloc(&h->kf_lcf, (size_t)(nk * win + kRecTail) * sizeof(float4)));
+    CU_TRY(h, cudaMalloc(&h->kf_lcp, (size_t)(nk * win + kRecTail) * sizeof(uint32_t)));
+    CU_TRY(h, cudaMemsetAsync(h->kf_lcf, 0, (size_t)(nk * win + kRecTail) * sizeof(float4), h->stream));
+    CU_TRY(h, cudaMemsetAsync(h->kf_lcp, 0, (size_t)(nk * win + kRecTail) * sizeof(uint32_t), h->stream));
     return ELLC_OK;
 }
 
@@ -404,7 +408,7 @@ static void fill_params(const ellc_handle* h, TrackParams& p) {
     p.tex_pool = h->fr_tex; p.tex_slot_stride = h->geo.win_off[kLevels] + kTexPad;
     p.geo_pool = h->kf_geo; p.pix_pool = h->kf_pix; p.ikf_pool = h->kf_ikf; p.rec_slot_stride = h->geo.win_off[kLevels];
     p.count_pool = h->kf_count;
-    p.frw_pool = h->fr_weight; p.lc_pool = h->kf_lc; p.lc_H = h->kf_lcH;
+    p.frw_pool = h->fr_weight; p.lc_pool = h->kf_lc; p.lc_H = h->kf_lcH; p.lcf_pool = h->kf_lcf; p.lcp_pool = h->kf_lcp;
     p.level_hi = kLevels - 1; p.level_lo = 0;
     p.pairs_per_cta = 1;
 }
@@ -1063,7 +1067,7 @@ int ellc_prepare_keyframes_lc(ellc_handle* h, int32_t n, const int32_t* kf_slots
     rc = stage_h2d(h, d_slots, kf_slots, (size_t)n * sizeof(int));
     if (rc) return rc;
     h->launches += launch_lc_prepare(h->stream, h->kf_geo, h->kf_pix, h->geo.win_off[kLevels], h->kf_count, h->kf_img, h->geo.img_off[kLevels],
-                                     h->kf_weight, h->kf_lc, h->kf_lcH, h->K, d_slots, n, h->geo);
+                                     h->kf_weight, h->kf_lc, h->kf_lcf, h->kf_lcp, h->kf_lcH, h->K, d_slots, n, h->geo);
     CU_TRY(h, cudaGetLastError());
     for (int i = 0; i < n; ++i) h->kf_lc_ready[kf_slots[i]] = 1;
     return ELLC_OK;

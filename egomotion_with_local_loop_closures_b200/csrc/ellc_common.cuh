@@ -109,6 +109,8 @@ struct TrackParams {
     float* weight_out;         // optional display_weightimg of the evaluated level (cols x rows), evaluate-only mode
     float* frw_pool;           // per frame slot: display_weightimg of every level (win layout) for ELLC_PAIR_SAVE_WEIGHTS pairs
     const LcRec* lc_pool;      // loop-closure records, per keyframe slot (rec_slot_stride)
+    const float4* lcf_pool;    // compact loop-closure records of the FAST flavour: {wX, wY, depth, weight} ...
+    const uint32_t* lcp_pool;  // ... + the keyframe pixel as a texel word (2 gradx + 512 : 10 | 2 grady + 512 : 10 | - | I : 8): 20 B / pixel
     const float* lc_H;         // [kf_slot][kLevels][kLcHStride]: hessian (36, src/PixelWisePyramid.cpp:938), hessianInv (36, :939), ok (1)
     uint32_t zero_mask;        // always 0: an opaque zero the pixel loop uses to build ordering dependences
 };

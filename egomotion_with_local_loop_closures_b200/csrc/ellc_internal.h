@@ -29,8 +29,8 @@ int launch_accumulate_weights(cudaStream_t st, float* kf_weight_slot, const uint
                               int64_t win, const int* d_frame_slots, int n);
 int launch_finalise_weights(cudaStream_t st, float* kf_weight_slot, const int counts[kLevels], const Geometry& geo);
 int launch_lc_prepare(cudaStream_t st, const SelGeo* geo_pool, const SelPix* pix_pool, int64_t rec_slot_stride, const int* count_pool,
-                      const uint8_t* img_pool, int64_t img_slot_stride, const float* weight_pool, LcRec* lc_pool, float* lc_H,
-                      const LevelK* K, const int* d_slots, int n, const Geometry& geo);
+                      const uint8_t* img_pool, int64_t img_slot_stride, const float* weight_pool, LcRec* lc_pool, float4* lcf_pool,
+                      uint32_t* lcp_pool, float* lc_H, const LevelK* K, const int* d_slots, int n, const Geometry& geo);
 // dst (device, 4-byte aligned, capacity rounded up to 4 bytes) <- pinned host memory read by the SMs (no copy engine)
 int launch_pull_host(cudaStream_t st, void* dst, const void* src_host_devptr, size_t bytes);
 

@@ -371,8 +371,8 @@ __global__ void __launch_bounds__(256) finalise_weights_kernel(float* __restrict
 __global__ void __launch_bounds__(256)
 lc_prepare_kernel(const SelGeo* __restrict__ geo_pool, const SelPix* __restrict__ pix_pool, int64_t rec_slot_stride,
                   const int* __restrict__ count_pool, const uint8_t* __restrict__ img_pool, int64_t img_slot_stride,
-                  const float* __restrict__ weight_pool, LcRec* __restrict__ lc_pool, float* __restrict__ lc_H, KSet ks,
-                  const int* __restrict__ slots, Geometry geo) {
+                  const float* __restrict__ weight_pool, LcRec* __restrict__ lc_pool, float4* __restrict__ lcf_pool,
+                  uint32_t* __restrict__ lcp_pool, float* __restrict__ lc_H, KSet ks, const int* __restrict__ slots, Geometry geo) {
     const int level = blockIdx.x, slot = slots[blockIdx.y];
     const LevelK K = ks.k[level];
     const int cols = geo.cols[level], rows = geo.rows[level], stride = geo.pyr_w[level];
@@ -386,7 +386,8 @@ lc_prepare_kernel(const SelGeo* __restrict__ geo_pool, const SelPix* __restrict_
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const SelPix px = pix_pool[rec_off + i];
         const int x = selpix_x(px), y = selpix_y(px);
-        const float dep = geo_pool[rec_off + i].depth;
+        const SelGeo sg = geo_pool[rec_off + i];
+        const float dep = sg.depth;
         // prev_frame->gradientx/y at (x, y): frame::calculateGradient, src/Frame.cpp:185-285
         const uint8_t* r = img + (int64_t)y * stride;
         const int c = r[x];
@@ -418,6 +419,11 @@ lc_prepare_kernel(const SelGeo* __restrict__ geo_pool, const SelPix* __restrict_
         rec.w = wimg[y * cols + x];                                                    // weight_pyramid[level] :668
         rec.pad = 0.f;
         lc_pool[rec_off + i] = rec;
+        // FAST flavour: 20 bytes instead of 52 -- the iteration rebuilds J from the keyframe pixel's gradients (kept exactly, as a
+        // texel word in the frame texel format) and the back-projected point; the loop-closure kernel streams these records from
+        // DRAM every iteration (the records of the resident keyframes are far larger than L2)
+        lcf_pool[rec_off + i] = make_float4(sg.wX, sg.wY, sg.depth, rec.w);
+        lcp_pool[rec_off + i] = (uint32_t)(gx2 + 512) | ((uint32_t)(gy2 + 512) << 10) | ((uint32_t)c << 24);
 #pragma unroll
         for (int a = 0; a < 6; ++a) {
             const double wj = (double)__fmul_rn(rec.J[a], rec.w);                      // weightedSteepestDescent :668-673
@@ -644,12 +650,12 @@ int launch_finalise_weights(cudaStream_t st, float* kf_weight_slot, const int co
 }
 
 int launch_lc_prepare(cudaStream_t st, const SelGeo* geo_pool, const SelPix* pix_pool, int64_t rec_slot_stride, const int* count_pool,
-                      const uint8_t* img_pool, int64_t img_slot_stride, const float* weight_pool, LcRec* lc_pool, float* lc_H,
-                      const LevelK* K, const int* d_slots, int n, const Geometry& geo) {
+                      const uint8_t* img_pool, int64_t img_slot_stride, const float* weight_pool, LcRec* lc_pool, float4* lcf_pool,
+                      uint32_t* lcp_pool, float* lc_H, const LevelK* K, const int* d_slots, int n, const Geometry& geo) {
     KSet ks;
     for (int l = 0; l < kLevels; ++l) ks.k[l] = K[l];
     lc_prepare_kernel<<<dim3(kLevels, n), 256, 0, st>>>(geo_pool, pix_pool, rec_slot_stride, count_pool, img_pool, img_slot_stride,
-                                                        weight_pool, lc_pool, lc_H, ks, d_slots, geo);
+                                                        weight_pool, lc_pool, lcf_pool, lcp_pool, lc_H, ks, d_slots, geo);
     return 1;
 }
 
