@@ -293,3 +293,34 @@ def test_reference_live_loop_closure_flow(oracle_mod, fx, parallel):
     for l in range(4):
         for o, q in zip(tr["levels"][l], r["lc_trace"]["levels"][l]):
             assert np.array_equal(np.asarray(o["H"], np.float32).reshape(6, 6), q["H"]) and np.array_equal(o["b"], q["b"]), l
+
+
+@live
+def test_reference_live_randomised_sweep(oracle_mod):
+    """Eight more seeded pairs with random ground-truth motions (0.3 - 4 degrees, up to 0.06 units) and random initial poses,
+    forward tracker: counts, iteration counts, every hessian / sd_param / weightedPose / pose bit-identical to the reference."""
+    import sys
+    sys.path.insert(0, GOLD)
+    from egomotion_with_local_loop_closures_b200 import synth
+    k = ref.dims()
+    kk = dict(fx=k["fx"], fy=k["fy"], cx=k["cx"], cy=k["cy"])
+    ocfg = oracle_mod.default_config(k["width"], k["height"], fx=float(k["fx"]), fy=float(k["fy"]), cx=float(k["cx"]), cy=float(k["cy"]))
+    rng = np.random.default_rng(2026)
+    total = 0
+    for scene_seed in (7, 19):
+        scene = synth.SynthScene(k["width"], k["height"], seed_tex=1000 + scene_seed, k=kk)
+        kf = scene.keyframe(noise_seed=scene_seed)
+        for _ in range(4):
+            gt = synth.random_pose(rng, rot=np.deg2rad(rng.uniform(0.3, 4.0)), trans=rng.uniform(0.005, 0.06))
+            cur = scene.render(synth.se3_exp(gt), noise_seed=int(rng.integers(1, 10**6)))
+            init = (gt * rng.uniform(0.0, 1.2) + rng.normal(0, 1e-3, 6)).astype(np.float32)
+            pose, tr = oracle_mod.track(ocfg, kf["image"], cur, kf["depth"], kf["var"], init)
+            r = ref.track_trace(kf["image"], cur, kf["depth"], kf["var"], init)
+            assert tr["n_selected"] == r["n_selected"] and tr["n_iters"] == r["n_iters"]
+            assert np.array_equal(pose, r["final_pose"])
+            for l in range(4):
+                for o, q in zip(tr["levels"][l], r["levels"][l]):
+                    assert np.array_equal(np.asarray(o["H"], np.float32).reshape(6, 6), q["H"]) and np.array_equal(o["b"], q["b"])
+                    assert np.float32(o["weighted_pose"]) == q["weighted_pose"] and np.array_equal(o["pose_after"], q["pose_after"])
+                    total += 1
+    assert total > 100
