@@ -268,11 +268,18 @@ class Tracker:
         pairs = np.ascontiguousarray(pairs, PAIR_DTYPE)
         dres = C.c_void_p()
         self._chk(lib().ellc_track_batch_async(self._h, len(pairs), _p(pairs), C.byref(dres)))
+        # host arrays of the uploads issued so far must outlive their copies: they are released when the records of this batch
+        # (which was enqueued behind those copies) have been fetched
+        self._keep_inflight = getattr(self, "_keep_inflight", [])
+        self._keep_inflight.append(getattr(self, "_keep", []))
+        self._keep = []
         return dres.value
 
     def results_download(self, device_ptr, n):
         res = np.zeros(n, RESULT_DTYPE)
         self._chk(lib().ellc_results_download(self._h, device_ptr, n, _p(res)))
+        if getattr(self, "_keep_inflight", None):
+            self._keep_inflight.pop(0)
         return res
 
     def gn_evaluate(self, kf_slot, frame_slot, level, pose, want_weights=False):
