@@ -18,12 +18,23 @@ def _stale():
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
+def source_hash():
+    """SHA-1 over the kernel / ABI sources: ellc_version() carries it, so that a profile (profiles/r02_traffic.json,
+    r02_sass_histogram.json) can be matched to the build it was taken from."""
+    import hashlib
+    h = hashlib.sha1()
+    for f in sorted(SOURCES + HEADERS):
+        with open(os.path.join(CSRC, f), "rb") as fh:
+            h.update(f.encode() + b"\0" + fh.read())
+    return h.hexdigest()[:12]
+
+
 def build(force=False, verbose=False):
     """Compile every CUDA source of the package for sm_100a into one shared library; returns its path."""
     if not (force or _stale()):
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    cmd = [nvcc] + NVCC_FLAGS + ["-DELLC_SRC_HASH=\"%s\"" % source_hash()] + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
     proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + proc.stdout + proc.stderr)

@@ -26,7 +26,8 @@ class Config(C.Structure):
                 ("max_iter", C.c_int32 * LEVELS), ("huber_d", C.c_float), ("camera_pixel_noise_2", C.c_float),
                 ("weight", C.c_float * 6), ("stop_threshold", C.c_float), ("arithmetic", C.c_int32),
                 ("jacobian_at_warped", C.c_int32), ("max_keyframes", C.c_int32), ("max_frames", C.c_int32),
-                ("ctas_per_pair", C.c_int32), ("device", C.c_int32), ("pairs_per_cta", C.c_int32)]
+                ("ctas_per_pair", C.c_int32), ("device", C.c_int32), ("pairs_per_cta", C.c_int32),
+                ("lm_lambda", C.c_float), ("lm_up", C.c_float), ("lm_down", C.c_float)]
 
 
 class Pair(C.Structure):
@@ -44,7 +45,8 @@ class Result(C.Structure):
 class IterTrace(C.Structure):
     _fields_ = [("H", C.c_float * 36), ("b", C.c_float * 6), ("delta", C.c_float * 6), ("weighted_pose", C.c_float),
                 ("pose_after", C.c_float * 6), ("res_sum", C.c_float), ("weight_sum", C.c_float),
-                ("n_oob", C.c_int32), ("executed", C.c_int32), ("pad", C.c_int32 * 5)]
+                ("n_oob", C.c_int32), ("executed", C.c_int32), ("lm_lambda", C.c_float), ("lm_rejected", C.c_int32),
+                ("pad", C.c_int32 * 3)]
 
 
 assert C.sizeof(Result) == 256 and C.sizeof(IterTrace) == 256 and C.sizeof(Pair) == 36
@@ -55,7 +57,7 @@ RESULT_DTYPE = np.dtype([("pose", "<f4", 6), ("H", "<f4", 21), ("b", "<f4", 6), 
                          ("weighted_pose", "<f4", 4), ("n_oob", "<i4", 4), ("status", "<i4"), ("reserved", "<i4", 6)])
 TRACE_DTYPE = np.dtype([("H", "<f4", 36), ("b", "<f4", 6), ("delta", "<f4", 6), ("weighted_pose", "<f4"),
                         ("pose_after", "<f4", 6), ("res_sum", "<f4"), ("weight_sum", "<f4"), ("n_oob", "<i4"),
-                        ("executed", "<i4"), ("pad", "<i4", 5)])
+                        ("executed", "<i4"), ("lm_lambda", "<f4"), ("lm_rejected", "<i4"), ("pad", "<i4", 3)])
 LC_CAND_DTYPE = np.dtype([("loop_frame_slot", "<i4"), ("test_frame_slot", "<i4"), ("loop_pose_world", "<f4", 6), ("test_pose_world", "<f4", 6)])
 LC_STATS_DTYPE = np.dtype([("match_value", "<f8"), ("rms_error", "<f4"), ("relative_view_angle", "<f4"), ("pass", "<i4"), ("reserved", "<i4")])
 assert LC_CAND_DTYPE.itemsize == 56 and LC_STATS_DTYPE.itemsize == 24
@@ -71,7 +73,11 @@ SYMBOLS = ["ellc_default_config", "ellc_create", "ellc_destroy", "ellc_last_erro
            "ellc_se3_exp", "ellc_launch_count", "ellc_reset_launch_count", "ellc_stream", "ellc_stream_of", "ellc_selftest_division", "ellc_reset_keyframe_weights", "ellc_accumulate_weights",
            "ellc_finalise_weights", "ellc_upload_keyframe_weights", "ellc_read_keyframe_weights", "ellc_read_frame_weights",
            "ellc_prepare_keyframes_lc", "ellc_frame_histograms", "ellc_lc_gate", "ellc_upload_keyframe_hypotheses", "ellc_read_keyframe_occupancy", "ellc_read_keyframe_depth", "ellc_last_track_kernel_ms",
-           "ellc_prepare_async", "ellc_batch_kernel_ms"]
+           "ellc_prepare_async", "ellc_batch_kernel_ms", "ellc_batch_interval_ms", "ellc_fence",
+           "ellc_exchange_create", "ellc_exchange_attach_ipc", "ellc_exchange_attach_local", "ellc_track_batch_exchange",
+           "ellc_exchange_wait", "ellc_exchange_destroy", "ellc_se3_exp_closed", "ellc_se3_log_closed"]
+MAX_RANKS = 8
+IPC_HANDLE_BYTES = 64
 
 _lib = None
 
@@ -134,6 +140,18 @@ def lib():
         L.ellc_batch_kernel_ms.restype = C.c_float
         L.ellc_batch_kernel_ms.argtypes = [C.c_void_p, C.c_int32]
         L.ellc_prepare_async.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
+        L.ellc_batch_interval_ms.restype = C.c_float
+        L.ellc_batch_interval_ms.argtypes = [C.c_void_p, C.c_int32]
+        L.ellc_fence.argtypes = [C.c_void_p]
+        L.ellc_exchange_create.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+        L.ellc_exchange_attach_ipc.argtypes = [C.c_void_p, C.c_void_p]
+        L.ellc_exchange_attach_local.argtypes = [C.c_void_p, C.c_void_p]
+        L.ellc_track_batch_exchange.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]
+        L.ellc_exchange_wait.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+        L.ellc_exchange_destroy.argtypes = [C.c_void_p]
+        L.ellc_se3_exp_closed.argtypes = [C.c_void_p] * 2
+        L.ellc_se3_log_closed.restype = C.c_int
+        L.ellc_se3_log_closed.argtypes = [C.c_void_p] * 2
         _lib = L
     return _lib
 
@@ -176,8 +194,24 @@ def se3_exp(pose):
     return out.reshape(4, 4)
 
 
+def se3_exp_closed(pose):
+    """The FAST flavour's closed-form exp(hat(pose)) (rows 0..2 + [0 0 0 1]); small rotations only."""
+    pose = np.ascontiguousarray(pose, np.float32)
+    out = np.empty(16, np.float32)
+    lib().ellc_se3_exp_closed(_p(pose), _p(out))
+    return out.reshape(4, 4)
+
+
+def se3_log_closed(T):
+    """The FAST flavour's closed-form logarithm of a rigid 4x4; None when the rotation is outside its small-angle range."""
+    T = np.ascontiguousarray(np.asarray(T, np.float32).reshape(16))
+    out = np.empty(6, np.float32)
+    ok = lib().ellc_se3_log_closed(_p(T), _p(out))
+    return out if ok == 1 else None
+
+
 class Tracker:
-    """Thin owner of one ellc_handle (one CUDA stream + device pools)."""
+    """Thin owner of one ellc_handle (CUDA streams + device pools)."""
 
     def __init__(self, cfg):
         self.cfg = cfg
@@ -420,6 +454,48 @@ class Tracker:
 
     def batch_kernel_ms(self, batches_ago=0):
         return lib().ellc_batch_kernel_ms(self._h, int(batches_ago))
+
+    def batch_interval_ms(self, batches_ago=0):
+        return lib().ellc_batch_interval_ms(self._h, int(batches_ago))
+
+    def fence(self):
+        self._chk(lib().ellc_fence(self._h))
+
+    # -- multi-GPU result exchange (NVLink peer memory)
+    def exchange_create(self, rank, world, capacity):
+        buf = np.zeros(IPC_HANDLE_BYTES, np.uint8)
+        self._chk(lib().ellc_exchange_create(self._h, int(rank), int(world), int(capacity), _p(buf)))
+        return buf
+
+    def exchange_attach_ipc(self, handles):
+        hs = np.ascontiguousarray(np.asarray(handles, np.uint8).reshape(-1))
+        self._chk(lib().ellc_exchange_attach_ipc(self._h, _p(hs)))
+
+    def exchange_attach_local(self, trackers):
+        arr = (C.c_void_p * len(trackers))(*[t._h for t in trackers])
+        self._chk(lib().ellc_exchange_attach_local(self._h, arr))
+
+    def track_batch_exchange(self, pairs, global_index, n_total, root=-1):
+        pairs = np.ascontiguousarray(pairs, PAIR_DTYPE)
+        gi = np.ascontiguousarray(global_index, np.int32)
+        assert len(gi) == len(pairs)
+        tok = C.c_int64()
+        self._chk(lib().ellc_track_batch_exchange(self._h, len(pairs), _p(pairs), _p(gi), int(n_total), int(root), C.byref(tok)))
+        self._keep_inflight = getattr(self, "_keep_inflight", [])
+        self._keep_inflight.append(getattr(self, "_keep", []))
+        self._keep = []
+        return tok.value
+
+    def exchange_wait(self, token, n_total=None, out=None):
+        """Wait for the batch `token`; on a receiving rank returns the n_total gathered records (global pair order)."""
+        res = out if out is not None else (np.zeros(n_total, RESULT_DTYPE) if n_total else None)
+        self._chk(lib().ellc_exchange_wait(self._h, int(token), _p(res) if res is not None else None))
+        if getattr(self, "_keep_inflight", None):
+            self._keep_inflight.pop(0)
+        return res
+
+    def exchange_destroy(self):
+        self._chk(lib().ellc_exchange_destroy(self._h))
 
     def prepare_async(self, frame_slots, kf_slots):
         """Preparation of these slots on the low-priority preparation stream (overlaps the batch that is tracking now)."""

@@ -11,12 +11,14 @@
 // Uploads only mark slots dirty; the pyramid / texel / selection kernels run batched over all dirty slots right before
 // the next consumer (track, evaluate, read-back) -- a whole batch costs 4 (frames) + 6 (keyframes) launches.
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "ellc_internal.h"
@@ -24,12 +26,44 @@
 
 using namespace ellc;
 
+// ---- multi-GPU result exchange (include/ellc_gn.h "result exchange") ------------------------------------------------
+// Every rank owns one block of device memory: a header of counters and a ring of kXchgRing result tables of `capacity` records.
+// Token t (the t-th exchanged batch, the same number on every rank) uses table t % kXchgRing everywhere.  A sender's tracking
+// kernel stores its records into the tables of the receiving ranks (peer memory mapped with CUDA IPC or, inside one process,
+// cudaDeviceEnablePeerAccess) and a one-warp kernel behind it adds its record count to the receivers' arrived[] counters; a
+// receiver's HOST polls its own counter, copies the table out and publishes released[] = t, which a sender reads (from the
+// receiver's memory) before it reuses that table for token t + kXchgRing.  No kernel ever spins.
+constexpr int kXchgRing = 4;
+struct XchgHeader {
+    unsigned long long arrived[kXchgRing];             // records delivered into table r, cumulative over the tokens that used it
+    unsigned long long released[kXchgRing];            // last token whose table r the owner has finished copying out
+    unsigned long long pad[32 - 2 * kXchgRing];
+};
+static_assert(sizeof(XchgHeader) == 256, "exchange header is one 256-byte record");
+struct ellc_exchange {
+    int rank, world, capacity;
+    void* block;                                       // own block (cudaMalloc)
+    void* peer_block[ELLC_MAX_RANKS];                  // every rank's block as mapped into this process (own: block)
+    bool peer_ipc[ELLC_MAX_RANKS];                     // opened with cudaIpcOpenMemHandle
+    bool attached;
+    long long token;                                   // tokens issued so far
+    unsigned long long expected[kXchgRing];            // records expected in the own table r, cumulative
+    struct Tok { long long seq; int n, n_total, root; } tok[kXchgRing];
+    unsigned long long** d_ctr;                        // device array [kXchgRing][ELLC_MAX_RANKS]: &header(d)->arrived[r]
+    unsigned long long* h_poll;                        // pinned scratch of the host polls
+};
 struct ellc_handle {
     ellc_config cfg;
     Geometry geo;
     LevelK K[kLevels];
     int rows_total;
-    cudaStream_t stream;                               // compute: prepare kernels, track kernel, small staging copies
+    cudaStream_t stream;                               // main compute stream: prepare kernels, evaluate, read-backs, small staging copies
+    cudaStream_t tstream[2];                           // tracking kernels: batch `seq` runs on tstream[seq & 1], so that the first CTAs of
+                                                       // batch k+1 fill the SMs the last wave of batch k leaves idle (the work distributor
+                                                       // dispatches the older kernel's CTAs first); both at the highest priority
+    cudaEvent_t main_ev;                               // recorded on the main stream at every batch launch; the batch's stream waits for it
+    cudaEvent_t hyp_ev; bool hyp_pending;              // depth pyramids built from hypotheses on the main stream (prep stream must wait)
+    bool overlap_batches;                              // ELLC_OVERLAP=0 serialises consecutive batches (A/B measurement)
     cudaStream_t copy_stream;                          // H2D uploads of images / depth / variance (overlap with compute)
     cudaStream_t d2h_stream;                           // result downloads of finished batches
     cudaEvent_t ev0r[4], ev1r[4];                      // track-kernel timing events of the last four batches (index: sequence & 3)
@@ -59,7 +93,12 @@ struct ellc_handle {
     std::vector<int> fr_dirty, kf_dirty;
     // staging
     int* d_slots; int slots_cap;
-    ellc_pair* d_pairs; ellc_result* d_results; ellc_result* d_results2[2]; int* d_order; int pairs_cap;
+    // per-batch staging / result buffers: ring of 4 by sequence number (two batches may be in flight, a third being staged, and the
+    // records of a finished one still being downloaded); entry r is reused by batch seq+4 after batch seq has completed
+    ellc_pair* d_pairs4[4]; ellc_result* d_results4[4]; int* d_order4[4]; int* d_gidx4[4]; int ring_cap[4]; long long res_seq[4];
+    ellc_pair* d_pairs; ellc_result* d_results; int* d_order;       // entry of the batch being launched / launched last
+    ellc_result* d_eval_result;                        // ellc_gn_evaluate's own record (never clobbers an undownloaded batch)
+    ellc_exchange* xc;                                 // multi-GPU result exchange (ellc_exchange_create), or null
     ellc_iter_trace* d_trace; int64_t trace_cap;
     float* d_small;                                    // 128 floats in/out for solve_update
     float* d_weight; int64_t weight_cap;
@@ -108,9 +147,14 @@ static void build_intrinsics(const ellc_config& c, LevelK K[kLevels]) {
     }
 }
 
+static void exchange_release(ellc_handle* h);
+
 extern "C" {
 
-const char* ellc_version(void) { return "ellc-gn-b200 0.1 (sm_100a)"; }
+#ifndef ELLC_SRC_HASH
+#define ELLC_SRC_HASH "unknown"
+#endif
+const char* ellc_version(void) { return "ellc-gn-b200 0.2 (sm_100a) src:" ELLC_SRC_HASH; }
 
 void ellc_default_config(ellc_config* c, int32_t width, int32_t height) {
     std::memset(c, 0, sizeof(*c));
@@ -125,6 +169,7 @@ void ellc_default_config(ellc_config* c, int32_t width, int32_t height) {
     c->jacobian_at_warped = 0;
     c->max_keyframes = 8; c->max_frames = 64;
     c->ctas_per_pair = 0; c->device = 0;
+    c->lm_lambda = 0.0f; c->lm_up = 4.0f; c->lm_down = 0.5f;                              // 0 = the reference's plain Gauss-Newton step
 }
 
 const char* ellc_last_error_string(const ellc_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
@@ -133,21 +178,26 @@ int ellc_destroy(ellc_handle* h) {
     if (!h) return ELLC_OK;
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    for (int i = 0; i < 2; ++i) if (h->tstream[i]) cudaStreamSynchronize(h->tstream[i]);
+    if (h->prep_stream) cudaStreamSynchronize(h->prep_stream);
+    exchange_release(h);
     if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
     if (h->d2h_stream) cudaStreamSynchronize(h->d2h_stream);
     cudaFree(h->fr_img); cudaFree(h->fr_tex); cudaFree(h->kf_img); cudaFree(h->kf_depth); cudaFree(h->kf_var);
     cudaFree(h->kf_mask); cudaFree(h->kf_geo); cudaFree(h->kf_pix); cudaFree(h->kf_ikf);
     cudaFree(h->d_hyp); cudaFree(h->d_nvalid); cudaFree(h->fr_hist);
     cudaFree(h->fr_weight); cudaFree(h->kf_weight); cudaFree(h->kf_lc); cudaFree(h->kf_lcH); cudaFree(h->kf_lcf); cudaFree(h->kf_lcp); cudaFree(h->kf_count); cudaFree(h->kf_rowcount); cudaFree(h->kf_rowoff);
-    cudaFree(h->d_slots); cudaFree(h->d_slots_p); cudaFree(h->d_pairs); cudaFree(h->d_results2[0]); cudaFree(h->d_results2[1]); cudaFree(h->d_order); cudaFree(h->d_trace); cudaFree(h->d_small);
+    cudaFree(h->d_slots); cudaFree(h->d_slots_p); cudaFree(h->d_trace); cudaFree(h->d_small); cudaFree(h->d_eval_result);
+    for (int r = 0; r < 4; ++r) { cudaFree(h->d_pairs4[r]); cudaFree(h->d_results4[r]); cudaFree(h->d_order4[r]); cudaFree(h->d_gidx4[r]); }
     cudaFree(h->d_weight);
     if (h->h_pin) cudaFreeHost(h->h_pin);
     if (h->ev_valid) {
         for (int i = 0; i < 4; ++i) { cudaEventDestroy(h->ev0r[i]); cudaEventDestroy(h->ev1r[i]); }
-        cudaEventDestroy(h->up_ev); cudaEventDestroy(h->prep_ev);
+        cudaEventDestroy(h->up_ev); cudaEventDestroy(h->prep_ev); cudaEventDestroy(h->main_ev); cudaEventDestroy(h->hyp_ev);
         for (int i = 0; i < 4; ++i) cudaEventDestroy(h->batch_ev[i]);
     }
     if (h->stream) cudaStreamDestroy(h->stream);
+    for (int i = 0; i < 2; ++i) if (h->tstream[i]) cudaStreamDestroy(h->tstream[i]);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
     if (h->prep_stream) cudaStreamDestroy(h->prep_stream);
@@ -201,12 +251,17 @@ int ellc_create(const ellc_config* cfg, ellc_handle** out) {
     int prio_least = 0, prio_greatest = 0;
     CR_TRY(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
     CR_TRY(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_greatest));
+    for (int i = 0; i < 2; ++i) CR_TRY(cudaStreamCreateWithPriority(&h->tstream[i], cudaStreamNonBlocking, prio_greatest));
+    h->overlap_batches = true;
+    if (const char* e = std::getenv("ELLC_OVERLAP")) h->overlap_batches = (*e != '0');
     CR_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     CR_TRY(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
     CR_TRY(cudaStreamCreateWithPriority(&h->prep_stream, cudaStreamNonBlocking, prio_least));
     for (int i = 0; i < 4; ++i) { CR_TRY(cudaEventCreate(&h->ev0r[i])); CR_TRY(cudaEventCreate(&h->ev1r[i])); }
     CR_TRY(cudaEventCreateWithFlags(&h->up_ev, cudaEventDisableTiming));
     CR_TRY(cudaEventCreateWithFlags(&h->prep_ev, cudaEventDisableTiming));
+    CR_TRY(cudaEventCreateWithFlags(&h->main_ev, cudaEventDisableTiming));
+    CR_TRY(cudaEventCreateWithFlags(&h->hyp_ev, cudaEventDisableTiming));
     for (int i = 0; i < 4; ++i) CR_TRY(cudaEventCreateWithFlags(&h->batch_ev[i], cudaEventDisableTiming));
     h->ev_valid = true;
     h->fr_reader.assign(cfg->max_frames, 0);
@@ -236,7 +291,8 @@ int ellc_create(const ellc_config* cfg, ellc_handle** out) {
     CR_TRY(cudaMalloc(&h->d_slots, 2 * h->slots_cap * sizeof(int)));
     CR_TRY(cudaMalloc(&h->d_slots_p, 2 * h->slots_cap * sizeof(int)));
     CR_TRY(cudaMalloc(&h->d_small, 128 * sizeof(float)));
-    h->pin_cap = 8 << 20;
+    CR_TRY(cudaMalloc(&h->d_eval_result, sizeof(ellc_result) + 256));
+    h->pin_cap = 32 << 20;
     CR_TRY(cudaHostAlloc(&h->h_pin, h->pin_cap, cudaHostAllocMapped));
     CR_TRY(cudaHostGetDevicePointer(&h->d_pin, h->h_pin, 0));
     h->pin_used = 0;
@@ -250,17 +306,29 @@ int ellc_create(const ellc_config* cfg, ellc_handle** out) {
 }  // extern "C"
 
 // ---- internal helpers ------------------------------------------------------------------------------------------------
-// Copy a small host payload to the device through the pinned arena (no implicit host/device serialisation).
+// Copy a small host payload to the device through the pinned arena (no implicit host/device serialisation).  The arena is a bump
+// allocator that is only ever rewound after EVERY stream that may still pull from it has been synchronised (here, when it is
+// full, and in ellc_synchronize): a pull kernel enqueued on the low-priority preparation stream, or behind an event on a tracking
+// stream, can run long after the call that staged its bytes has returned.
+static int sync_all_streams(ellc_handle* h) {
+    CU_TRY(h, cudaStreamSynchronize(h->copy_stream));
+    CU_TRY(h, cudaStreamSynchronize(h->prep_stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < 2; ++i) CU_TRY(h, cudaStreamSynchronize(h->tstream[i]));
+    CU_TRY(h, cudaStreamSynchronize(h->d2h_stream));
+    h->batch_done_seq = h->batch_seq;
+    h->pin_used = 0;
+    return ELLC_OK;
+}
 static int stage_h2d_on(ellc_handle* h, cudaStream_t st, void* dst, const void* src, size_t bytes) {
-    if (bytes > h->pin_cap / 2) {           // large payload: plain (staged) async copy
+    if (bytes > h->pin_cap / 4) {           // large payload: plain (staged) async copy
         CU_TRY(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
         return ELLC_OK;
     }
     const size_t aligned = (bytes + 255) & ~(size_t)255;
     if (h->pin_used + aligned > h->pin_cap) {
-        CU_TRY(h, cudaStreamSynchronize(h->prep_stream));
-        CU_TRY(h, cudaStreamSynchronize(h->stream));
-        h->pin_used = 0;
+        int rc = sync_all_streams(h);
+        if (rc) return rc;
     }
     void* p = (char*)h->h_pin + h->pin_used;
     std::memcpy(p, src, bytes);
@@ -272,12 +340,24 @@ static int stage_h2d_on(ellc_handle* h, cudaStream_t st, void* dst, const void* 
 }
 static int stage_h2d(ellc_handle* h, void* dst, const void* src, size_t bytes) { return stage_h2d_on(h, h->stream, dst, src, bytes); }
 
+// batch_done_seq: every batch up to and including this sequence number is known to be complete
+static void note_done(ellc_handle* h, long long seq) {
+    if (seq == h->batch_done_seq + 1) h->batch_done_seq = seq;
+}
+// Work on the main stream that reads or writes slot data is ordered behind the (up to two) tracking batches in flight on the
+// tracking streams.  The pipelined preparation paths (flush_dirty's side path, ellc_prepare_async) do NOT call this: they order
+// themselves behind the last batch that READ their slots only.
+static int main_waits_batches(ellc_handle* h) {
+    for (long long q = h->batch_seq; q >= 1 && q > h->batch_seq - 2; --q)
+        if (q > h->batch_done_seq) CU_TRY(h, cudaStreamWaitEvent(h->stream, h->batch_ev[q & 3], 0));
+    return ELLC_OK;
+}
 
-// An upload overwrites a slot on copy_stream.  It must not pass a track batch (compute stream) that still reads the slot:
+// An upload overwrites a slot on copy_stream.  It must not pass a track batch that still reads the slot:
 // wait for that batch's completion event, unless it is already known to be finished.
 static int guard_slot_write(ellc_handle* h, long long reader_seq) {
     if (reader_seq <= h->batch_done_seq) return ELLC_OK;
-    if (reader_seq + 4 <= h->batch_seq) { h->batch_done_seq = reader_seq; return ELLC_OK; }   // ring slot recycled => batch finished
+    if (reader_seq + 4 <= h->batch_seq) return ELLC_OK;                        // ring entry recycled => that batch was waited for
     CU_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->batch_ev[reader_seq & 3], 0));
     return ELLC_OK;
 }
@@ -287,19 +367,19 @@ static int after_upload(ellc_handle* h) {
     return ELLC_OK;
 }
 
-static int ensure_pairs_cap(ellc_handle* h, int n, bool want_trace) {
-    if (n > h->pairs_cap) {
-        CU_TRY(h, cudaStreamSynchronize(h->stream));
-        CU_TRY(h, cudaStreamSynchronize(h->d2h_stream));
-        cudaFree(h->d_pairs); cudaFree(h->d_results2[0]); cudaFree(h->d_results2[1]); cudaFree(h->d_order);
-        h->d_pairs = nullptr; h->d_results = h->d_results2[0] = h->d_results2[1] = nullptr; h->d_order = nullptr; h->pairs_cap = 0;
+// Ring entry r = seq & 3 of the per-batch buffers; the caller has already waited for batch seq - 4, the previous user of the entry.
+// Growing it frees that batch's records: a pointer returned by ellc_track_batch_async is valid until three more batches have
+// been launched (include/ellc_gn.h).
+static int ensure_ring_cap(ellc_handle* h, int r, int n, bool want_trace) {
+    if (n > h->ring_cap[r]) {
+        cudaFree(h->d_pairs4[r]); cudaFree(h->d_results4[r]); cudaFree(h->d_order4[r]); cudaFree(h->d_gidx4[r]);
+        h->d_pairs4[r] = nullptr; h->d_results4[r] = nullptr; h->d_order4[r] = nullptr; h->d_gidx4[r] = nullptr; h->ring_cap[r] = 0;
         int cap = n < 256 ? 256 : n;
-        CU_TRY(h, cudaMalloc(&h->d_pairs, (size_t)cap * sizeof(ellc_pair)));
-        CU_TRY(h, cudaMalloc(&h->d_results2[0], (size_t)cap * sizeof(ellc_result)));
-        CU_TRY(h, cudaMalloc(&h->d_results2[1], (size_t)cap * sizeof(ellc_result)));
-        h->d_results = h->d_results2[0];
-        CU_TRY(h, cudaMalloc(&h->d_order, (size_t)cap * sizeof(int)));
-        h->pairs_cap = cap;
+        CU_TRY(h, cudaMalloc(&h->d_pairs4[r], (size_t)cap * sizeof(ellc_pair)));
+        CU_TRY(h, cudaMalloc(&h->d_results4[r], (size_t)cap * sizeof(ellc_result)));
+        CU_TRY(h, cudaMalloc(&h->d_order4[r], (size_t)cap * sizeof(int)));
+        CU_TRY(h, cudaMalloc(&h->d_gidx4[r], (size_t)cap * sizeof(int)));
+        h->ring_cap[r] = cap;
     }
     if (want_trace) {
         const int64_t need = (int64_t)n * kLevels * ELLC_MAX_TRACE_ITERS;
@@ -317,7 +397,9 @@ static int prepare_frames_impl(ellc_handle* h, int n, const int* slots, bool sid
     if (n <= 0) return ELLC_OK;
     cudaStream_t st = side ? h->prep_stream : h->stream;
     int* d_slots = side ? h->d_slots_p : h->d_slots;
-    int rc = stage_h2d_on(h, st, d_slots, slots, (size_t)n * sizeof(int));
+    int rc = side ? ELLC_OK : main_waits_batches(h);
+    if (rc) return rc;
+    rc = stage_h2d_on(h, st, d_slots, slots, (size_t)n * sizeof(int));
     if (rc) return rc;
     h->launches += launch_pyramid(st, h->fr_img, h->geo.img_off[kLevels], d_slots, n, h->geo);
     h->launches += launch_pack_tex(st, h->fr_img, h->geo.img_off[kLevels], h->fr_tex, h->geo.win_off[kLevels] + kTexPad,
@@ -331,7 +413,9 @@ static int prepare_keyframes_impl(ellc_handle* h, int n, const int* slots, bool 
     if (n <= 0) return ELLC_OK;
     cudaStream_t st = side ? h->prep_stream : h->stream;
     int* d_slots = (side ? h->d_slots_p : h->d_slots) + h->slots_cap;
-    int rc = stage_h2d_on(h, st, d_slots, slots, (size_t)n * sizeof(int));
+    int rc = side ? ELLC_OK : main_waits_batches(h);
+    if (rc) return rc;
+    rc = stage_h2d_on(h, st, d_slots, slots, (size_t)n * sizeof(int));
     if (rc) return rc;
     h->launches += launch_pyramid(st, h->kf_img, h->geo.img_off[kLevels], d_slots, n, h->geo);
     h->launches += launch_select(st, h->kf_depth, h->kf_var, h->geo.win_off[kLevels], h->kf_img,
@@ -352,6 +436,10 @@ static int flush_dirty(ellc_handle* h) {
     if (h->uploads_pending) {                              // copy_stream is in order: the last upload's event covers them all
         CU_TRY(h, cudaStreamWaitEvent(side ? h->prep_stream : h->stream, h->up_ev, 0));
         h->uploads_pending = false;
+    }
+    if (h->hyp_pending) {                                  // depth / variance pyramids a hypothesis upload is still building on the main stream
+        if (side) CU_TRY(h, cudaStreamWaitEvent(h->prep_stream, h->hyp_ev, 0));
+        h->hyp_pending = false;
     }
     if (!h->fr_dirty.empty()) {
         std::vector<int> s;
@@ -411,6 +499,9 @@ static void fill_params(const ellc_handle* h, TrackParams& p) {
     p.frw_pool = h->fr_weight; p.lc_pool = h->kf_lc; p.lc_H = h->kf_lcH; p.lcf_pool = h->kf_lcf; p.lcp_pool = h->kf_lcp;
     p.level_hi = kLevels - 1; p.level_lo = 0;
     p.pairs_per_cta = 1;
+    p.lm_lambda = h->cfg.lm_lambda > 0.f ? h->cfg.lm_lambda : 0.f;
+    p.lm_up = h->cfg.lm_up > 1.f ? h->cfg.lm_up : 4.0f;
+    p.lm_down = (h->cfg.lm_down > 0.f && h->cfg.lm_down <= 1.f) ? h->cfg.lm_down : 0.5f;
 }
 
 static int pick_cluster(const ellc_handle* h, int n) {
@@ -455,24 +546,39 @@ static int validate_pairs(ellc_handle* h, int n, const ellc_pair* pairs) {
     return ELLC_OK;
 }
 
-static int track_launch(ellc_handle* h, int n, const ellc_pair* pairs, bool want_trace) {
+// Launch parameters of the optional result exchange of a batch (ellc_track_batch_exchange)
+struct XchgLaunch {
+    int n_dst = 0;
+    ellc_result* dst[ELLC_MAX_RANKS] = {};
+    const int32_t* global_index = nullptr;                 // host
+};
+
+static int track_launch(ellc_handle* h, int n, const ellc_pair* pairs, bool want_trace, const XchgLaunch* xl = nullptr) {
     int rc = validate_pairs(h, n, pairs);
     if (rc) return rc;
     CU_TRY(h, cudaSetDevice(h->cfg.device));
     rc = flush_dirty(h);
     if (rc) return rc;
-    rc = ensure_pairs_cap(h, n, want_trace);
+    // batch bookkeeping: sequence number, ring entry (staging + result buffers: a finished batch can be downloaded while the next two
+    // run), completion event (ring of 4: reusing an entry requires its old batch to be finished)
+    const long long seq = h->batch_seq + 1;
+    const int r = (int)(seq & 3);
+    if (seq > 4 && seq - 4 > h->batch_done_seq) {
+        CU_TRY(h, cudaEventSynchronize(h->batch_ev[r]));
+        if (seq - 4 > h->batch_done_seq) h->batch_done_seq = seq - 4;          // batches complete in order of their streams' events
+    }
+    rc = ensure_ring_cap(h, r, n, want_trace);
     if (rc) return rc;
-    rc = stage_h2d(h, h->d_pairs, pairs, (size_t)n * sizeof(ellc_pair));
-    if (rc) return rc;
+    h->d_pairs = h->d_pairs4[r]; h->d_order = h->d_order4[r]; h->d_results = h->d_results4[r];
+    cudaStream_t ts = h->tstream[seq & 1];
     // Schedule: frame-major, keyframe-minor.  Pairs are independent, so the order is free; putting the K pairs of one
     // frame on adjacent CTAs makes them share that frame's texel pyramid in L2 (and, with few keyframes, the keyframe
     // selection lists stay L2-resident as well).  Results are still written at the caller's pair index.
     // Constant-weight (loop-closure) pairs run in their own kernel: the schedule lists the forward pairs first.
     int n_fwd = 0;
     bool save_weights = false;
+    std::vector<int> order(n);
     {
-        std::vector<int> order(n);
         for (int i = 0; i < n; ++i) order[i] = i;
         int kf_group = 0;                                  // EXPERIMENT: keyframes per schedule group (0 = frame-major over all keyframes)
         if (const char* e = std::getenv("ELLC_ORDER_KF_GROUP")) kf_group = std::atoi(e);
@@ -490,26 +596,36 @@ static int track_launch(ellc_handle* h, int n, const ellc_pair* pairs, bool want
             if (!(pairs[i].flags & ELLC_PAIR_CONST_WEIGHT)) ++n_fwd;
             if (pairs[i].flags & ELLC_PAIR_SAVE_WEIGHTS) save_weights = true;
         }
-        rc = stage_h2d(h, h->d_order, order.data(), (size_t)n * sizeof(int));
-        if (rc) return rc;
     }
     if (save_weights || n_fwd < n) {
         rc = ensure_lc_pools(h);
         if (rc) return rc;
     }
-    if (want_trace) CU_TRY(h, cudaMemsetAsync(h->d_trace, 0, (size_t)n * kLevels * ELLC_MAX_TRACE_ITERS * sizeof(ellc_iter_trace), h->stream));
-    // batch bookkeeping: sequence number, result buffer (two alternate, so a finished batch can be downloaded while the
-    // next one runs), completion event (ring of 4: reusing an entry requires its old batch to be finished)
-    const long long seq = h->batch_seq + 1;
-    if (seq > 4 && seq - 4 > h->batch_done_seq) {
-        CU_TRY(h, cudaEventSynchronize(h->batch_ev[seq & 3]));
-        h->batch_done_seq = seq - 4;
+    // Ordering of the batch's stream: behind everything enqueued on the main stream so far (synchronous preparation, weight
+    // and loop-closure kernels, and -- through the main stream's wait on prep_ev -- the pipelined preparation); NOT behind the
+    // previous batch, which runs on the other tracking stream, unless this batch shares buffers with it (trace, weight images).
+    CU_TRY(h, cudaEventRecord(h->main_ev, h->stream));
+    CU_TRY(h, cudaStreamWaitEvent(ts, h->main_ev, 0));
+    const bool serial = !h->overlap_batches || want_trace || save_weights || n_fwd < n;
+    if (serial && seq > 1 && seq - 1 > h->batch_done_seq) CU_TRY(h, cudaStreamWaitEvent(ts, h->batch_ev[(seq - 1) & 3], 0));
+    rc = stage_h2d_on(h, ts, h->d_pairs, pairs, (size_t)n * sizeof(ellc_pair));
+    if (rc) return rc;
+    rc = stage_h2d_on(h, ts, h->d_order, order.data(), (size_t)n * sizeof(int));
+    if (rc) return rc;
+    if (xl && xl->n_dst > 0) {
+        rc = stage_h2d_on(h, ts, h->d_gidx4[r], xl->global_index, (size_t)n * sizeof(int));
+        if (rc) return rc;
     }
-    h->d_results = h->d_results2[seq & 1];
+    if (want_trace) CU_TRY(h, cudaMemsetAsync(h->d_trace, 0, (size_t)n * kLevels * ELLC_MAX_TRACE_ITERS * sizeof(ellc_iter_trace), ts));
     TrackParams p;
     fill_params(h, p);
     p.pairs = h->d_pairs; p.order = h->d_order; p.results = h->d_results; p.trace = want_trace ? h->d_trace : nullptr; p.n_pairs = n;
-    CU_TRY(h, cudaEventRecord(h->ev0r[seq & 3], h->stream));
+    if (xl && xl->n_dst > 0) {
+        p.xchg_n = xl->n_dst;
+        for (int d = 0; d < xl->n_dst; ++d) p.xchg_dst[d] = xl->dst[d];
+        p.xchg_index = h->d_gidx4[r];
+    }
+    CU_TRY(h, cudaEventRecord(h->ev0r[r], ts));
     p.n_pairs = n_fwd;
     const int cluster = pick_cluster(h, n_fwd);
     p.pairs_per_cta = pick_pairs_per_cta(h, n_fwd, cluster);
@@ -517,24 +633,21 @@ static int track_launch(ellc_handle* h, int n, const ellc_pair* pairs, bool want
     if (const char* e = std::getenv("ELLC_DEBUG_NO_UPDATE")) if (*e == '1') p.no_update = 1;
     if (const char* e = std::getenv("ELLC_DEBUG_MAX_ITER")) std::sscanf(e, "%d,%d,%d,%d", &p.max_iter[0], &p.max_iter[1], &p.max_iter[2], &p.max_iter[3]);
     if (const char* e = std::getenv("ELLC_DEBUG_NO_STOP")) if (*e == '1') p.stop_threshold = -1.0f;
-    // Scheduling of the forward pairs: a cluster of CTAs per pair (few pairs), one CTA per 1..4 lockstep pairs, or (diagnostic,
-    // ELLC_SCHED=ws) the warp-specialised kernel whose solver warp overlaps K5 with the other pair's K4.
-    bool ws = false;                                       // measured slower than one CTA per pair on the B200 (see gn_track_ws_kernel)
-    if (const char* e = std::getenv("ELLC_SCHED")) ws = (cluster == 1) && (std::string(e) == "ws");
-    int l = ws ? launch_track_ws(h->stream, p, h->cfg.arithmetic == ELLC_ARITH_STRICT)
-               : launch_track(h->stream, p, cluster, h->cfg.arithmetic == ELLC_ARITH_STRICT);
+    // Scheduling of the forward pairs: a cluster of CTAs per pair (few pairs: latency) or one CTA per 1..4 lockstep pairs
+    int l = launch_track(ts, p, cluster, h->cfg.arithmetic == ELLC_ARITH_STRICT);
     if (l < 0) { h->err = std::string("track kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()); return ELLC_ERR_CUDA; }
     h->launches += l;
     if (n_fwd < n) {
         p.order = h->d_order + n_fwd;
         p.n_pairs = n - n_fwd;
-        l = launch_track_lc(h->stream, p, h->cfg.arithmetic == ELLC_ARITH_STRICT);
+        l = launch_track_lc(ts, p, h->cfg.arithmetic == ELLC_ARITH_STRICT);
         if (l < 0) { h->err = std::string("loop-closure track kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()); return ELLC_ERR_CUDA; }
         h->launches += l;
     }
-    CU_TRY(h, cudaEventRecord(h->ev1r[seq & 3], h->stream));
-    CU_TRY(h, cudaEventRecord(h->batch_ev[seq & 3], h->stream));
+    CU_TRY(h, cudaEventRecord(h->ev1r[r], ts));
+    CU_TRY(h, cudaEventRecord(h->batch_ev[r], ts));
     h->batch_seq = seq;
+    h->res_seq[r] = seq;
     for (int i = 0; i < n; ++i) { h->fr_reader[pairs[i].frame_slot] = seq; h->kf_reader[pairs[i].kf_slot] = seq; }
     CU_TRY(h, cudaGetLastError());
     return ELLC_OK;
@@ -606,10 +719,15 @@ int ellc_upload_keyframe_hypotheses(ellc_handle* h, int32_t slot, const uint8_t*
     rc = after_upload(h);
     if (rc) return rc;
     CU_TRY(h, cudaStreamWaitEvent(h->stream, h->up_ev, 0));
+    rc = main_waits_batches(h);                            // a batch in flight may still read this slot's depth / variance
+    if (rc) return rc;
     CU_TRY(h, cudaMemsetAsync(h->d_nvalid + slot, 0, sizeof(int), h->stream));
     h->launches += launch_depth_pyramid(h->stream, d_valid, d_idepth, d_vars, h->kf_depth + slot * win, h->kf_var + slot * win,
                                         valid_out ? d_vout : nullptr, h->d_nvalid + slot, h->geo);
     CU_TRY(h, cudaGetLastError());
+    // the pipelined preparation (flush_dirty's side path, ellc_prepare_async) runs on its own stream: it must see these pyramids
+    CU_TRY(h, cudaEventRecord(h->hyp_ev, h->stream));
+    h->hyp_pending = true;
     if (valid_out) {
         CU_TRY(h, cudaMemcpyAsync(valid_out, d_vout, (size_t)npx, cudaMemcpyDeviceToHost, h->stream));
         CU_TRY(h, cudaStreamSynchronize(h->stream));
@@ -644,6 +762,7 @@ int ellc_read_keyframe_depth(ellc_handle* h, int32_t slot, int32_t level, float*
     if (h->kf_state[slot] == 0) { h->err = "keyframe slot empty"; return ELLC_ERR_NOT_READY; }
     CU_TRY(h, cudaSetDevice(h->cfg.device));
     CU_TRY(h, cudaStreamSynchronize(h->copy_stream));
+    { int rcw = main_waits_batches(h); if (rcw) return rcw; }
     const int64_t win = h->geo.win_off[kLevels];
     const size_t bytes = (size_t)(h->geo.win_off[level + 1] - h->geo.win_off[level]) * sizeof(float);
     if (depth) CU_TRY(h, cudaMemcpyAsync(depth, h->kf_depth + slot * win + h->geo.win_off[level], bytes, cudaMemcpyDeviceToHost, h->stream));
@@ -719,15 +838,23 @@ int ellc_keyframe_devptrs(ellc_handle* h, int32_t slot, uint8_t** image, float**
 
 int ellc_prepare_frames(ellc_handle* h, int32_t n, const int32_t* slots) {
     if (!h || (n > 0 && !slots) || n > h->cfg.max_frames) return ELLC_ERR_INVALID;
-    for (int i = 0; i < n; ++i) if (slots[i] < 0 || slots[i] >= h->cfg.max_frames) { h->err = "frame slot out of range"; return ELLC_ERR_INVALID; }
+    for (int i = 0; i < n; ++i) {
+        if (slots[i] < 0 || slots[i] >= h->cfg.max_frames) { h->err = "frame slot out of range"; return ELLC_ERR_INVALID; }
+        if (h->fr_state[slots[i]] == 0) { h->err = "frame slot empty"; return ELLC_ERR_NOT_READY; }
+    }
     CU_TRY(h, cudaSetDevice(h->cfg.device));
+    if (h->uploads_pending) CU_TRY(h, cudaStreamWaitEvent(h->stream, h->up_ev, 0));    // uploads run on the copy stream (the flag stays: other consumers wait too)
     return prepare_frames_impl(h, n, slots);
 }
 
 int ellc_prepare_keyframes(ellc_handle* h, int32_t n, const int32_t* slots) {
     if (!h || (n > 0 && !slots) || n > h->cfg.max_keyframes) return ELLC_ERR_INVALID;
-    for (int i = 0; i < n; ++i) if (slots[i] < 0 || slots[i] >= h->cfg.max_keyframes) { h->err = "keyframe slot out of range"; return ELLC_ERR_INVALID; }
+    for (int i = 0; i < n; ++i) {
+        if (slots[i] < 0 || slots[i] >= h->cfg.max_keyframes) { h->err = "keyframe slot out of range"; return ELLC_ERR_INVALID; }
+        if (h->kf_state[slots[i]] == 0) { h->err = "keyframe slot empty"; return ELLC_ERR_NOT_READY; }
+    }
     CU_TRY(h, cudaSetDevice(h->cfg.device));
+    if (h->uploads_pending) CU_TRY(h, cudaStreamWaitEvent(h->stream, h->up_ev, 0));
     return prepare_keyframes_impl(h, n, slots);
 }
 
@@ -752,10 +879,9 @@ int ellc_prepare_async(ellc_handle* h, int32_t n_frames, const int32_t* frame_sl
     }
     CU_TRY(h, cudaSetDevice(h->cfg.device));
     if (h->uploads_pending) CU_TRY(h, cudaStreamWaitEvent(h->prep_stream, h->up_ev, 0));   // (the flag stays: other consumers wait too)
-    if (reader > h->batch_done_seq) {
-        if (reader + 4 <= h->batch_seq) h->batch_done_seq = reader;                          // its ring entry was recycled => finished
-        else CU_TRY(h, cudaStreamWaitEvent(h->prep_stream, h->batch_ev[reader & 3], 0));
-    }
+    if (h->hyp_pending) CU_TRY(h, cudaStreamWaitEvent(h->prep_stream, h->hyp_ev, 0));       // depth pyramids from hypotheses (main stream)
+    if (reader > h->batch_done_seq && reader + 4 > h->batch_seq)                            // (an older ring entry was recycled => finished)
+        CU_TRY(h, cudaStreamWaitEvent(h->prep_stream, h->batch_ev[reader & 3], 0));
     int rc = prepare_frames_impl(h, n_frames, frame_slots, true);
     if (rc) return rc;
     rc = prepare_keyframes_impl(h, n_keyframes, kf_slots, true);
@@ -768,13 +894,13 @@ int ellc_prepare_async(ellc_handle* h, int32_t n_frames, const int32_t* frame_sl
 int ellc_synchronize(ellc_handle* h) {
     if (!h) return ELLC_ERR_INVALID;
     CU_TRY(h, cudaSetDevice(h->cfg.device));
-    CU_TRY(h, cudaStreamSynchronize(h->copy_stream));
-    CU_TRY(h, cudaStreamSynchronize(h->prep_stream));
-    CU_TRY(h, cudaStreamSynchronize(h->stream));
-    CU_TRY(h, cudaStreamSynchronize(h->d2h_stream));
-    h->batch_done_seq = h->batch_seq;
-    h->pin_used = 0;
-    return ELLC_OK;
+    return sync_all_streams(h);
+}
+
+int ellc_fence(ellc_handle* h) {
+    if (!h) return ELLC_ERR_INVALID;
+    CU_TRY(h, cudaSetDevice(h->cfg.device));
+    return main_waits_batches(h);
 }
 
 int ellc_track_batch_async(ellc_handle* h, int32_t n, const ellc_pair* pairs, const ellc_result** device_results) {
@@ -791,18 +917,16 @@ int ellc_results_download(ellc_handle* h, const ellc_result* device_results, int
     if (n < 0 || (n > 0 && (!device_results || !results))) { h->err = "bad download arguments"; return ELLC_ERR_INVALID; }
     if (n == 0) return ELLC_OK;
     int which = -1;
-    for (int b = 0; b < 2; ++b) if (device_results == h->d_results2[b]) which = b;
-    if (which < 0) { h->err = "pointer was not returned by ellc_track_batch_async"; return ELLC_ERR_INVALID; }
+    for (int r = 0; r < 4; ++r) if (device_results == h->d_results4[r]) which = r;
+    if (which < 0) { h->err = "pointer was not returned by ellc_track_batch_async (or its buffer has been recycled)"; return ELLC_ERR_INVALID; }
     CU_TRY(h, cudaSetDevice(h->cfg.device));
-    // the batch that filled this buffer: the most recent sequence number with that parity
-    long long seq = h->batch_seq;
-    if ((seq & 1) != which) seq -= 1;
+    const long long seq = h->res_seq[which];               // the batch that filled this buffer last
     if (seq < 1) { h->err = "no batch has used this buffer yet"; return ELLC_ERR_NOT_READY; }
+    if (n > h->ring_cap[which]) { h->err = "more records requested than the batch held"; return ELLC_ERR_INVALID; }
     CU_TRY(h, cudaStreamWaitEvent(h->d2h_stream, h->batch_ev[seq & 3], 0));
     CU_TRY(h, cudaMemcpyAsync(results, device_results, (size_t)n * sizeof(ellc_result), cudaMemcpyDeviceToHost, h->d2h_stream));
     CU_TRY(h, cudaStreamSynchronize(h->d2h_stream));
-    if (seq > h->batch_done_seq) h->batch_done_seq = seq;
-    if (seq == h->batch_seq) h->pin_used = 0;              // nothing enqueued on the compute stream is still pending
+    note_done(h, seq);
     return ELLC_OK;
 }
 
@@ -812,12 +936,12 @@ int ellc_track_batch(ellc_handle* h, int32_t n, const ellc_pair* pairs, ellc_res
     if (n == 0) return ELLC_OK;
     int rc = track_launch(h, n, pairs, trace != nullptr);
     if (rc) return rc;
-    CU_TRY(h, cudaMemcpyAsync(results, h->d_results, (size_t)n * sizeof(ellc_result), cudaMemcpyDeviceToHost, h->stream));
+    cudaStream_t ts = h->tstream[h->batch_seq & 1];
+    CU_TRY(h, cudaMemcpyAsync(results, h->d_results, (size_t)n * sizeof(ellc_result), cudaMemcpyDeviceToHost, ts));
     if (trace) CU_TRY(h, cudaMemcpyAsync(trace, h->d_trace, (size_t)n * kLevels * ELLC_MAX_TRACE_ITERS * sizeof(ellc_iter_trace),
-                                         cudaMemcpyDeviceToHost, h->stream));
-    CU_TRY(h, cudaStreamSynchronize(h->stream));
-    h->batch_done_seq = h->batch_seq;
-    h->pin_used = 0;
+                                         cudaMemcpyDeviceToHost, ts));
+    CU_TRY(h, cudaStreamSynchronize(ts));
+    note_done(h, h->batch_seq);
     return ELLC_OK;
 }
 
@@ -833,9 +957,16 @@ int ellc_gn_evaluate(ellc_handle* h, int32_t kf_slot, int32_t frame_slot, int32_
     CU_TRY(h, cudaSetDevice(h->cfg.device));
     rc = flush_dirty(h);
     if (rc) return rc;
-    rc = ensure_pairs_cap(h, 1, true);
+    rc = main_waits_batches(h);
     if (rc) return rc;
-    rc = stage_h2d(h, h->d_pairs, &pr, sizeof(pr));
+    if (h->trace_cap < (int64_t)kLevels * ELLC_MAX_TRACE_ITERS) {
+        cudaFree(h->d_trace); h->d_trace = nullptr; h->trace_cap = 0;
+        CU_TRY(h, cudaMalloc(&h->d_trace, (size_t)kLevels * ELLC_MAX_TRACE_ITERS * sizeof(ellc_iter_trace)));
+        h->trace_cap = (int64_t)kLevels * ELLC_MAX_TRACE_ITERS;
+    }
+    // the evaluation has its own pair / result record (behind the record in d_eval_result): it never touches a batch's buffers
+    ellc_pair* d_pair = reinterpret_cast<ellc_pair*>(reinterpret_cast<char*>(h->d_eval_result) + sizeof(ellc_result));
+    rc = stage_h2d(h, d_pair, &pr, sizeof(pr));
     if (rc) return rc;
     const int64_t npx = (int64_t)h->geo.cols[level] * h->geo.rows[level];
     if (weight_image) {
@@ -849,7 +980,7 @@ int ellc_gn_evaluate(ellc_handle* h, int32_t kf_slot, int32_t frame_slot, int32_
     CU_TRY(h, cudaMemsetAsync(h->d_trace, 0, (size_t)kLevels * ELLC_MAX_TRACE_ITERS * sizeof(ellc_iter_trace), h->stream));
     TrackParams p;
     fill_params(h, p);
-    p.pairs = h->d_pairs; p.results = h->d_results; p.trace = h->d_trace; p.n_pairs = 1;
+    p.pairs = d_pair; p.results = h->d_eval_result; p.trace = h->d_trace; p.n_pairs = 1;
     p.level_hi = p.level_lo = level; p.iter_limit = 1; p.no_update = 1;
     p.weight_out = weight_image ? h->d_weight : nullptr;
     const int l = launch_track(h->stream, p, pick_cluster(h, 1), h->cfg.arithmetic == ELLC_ARITH_STRICT);
@@ -858,7 +989,6 @@ int ellc_gn_evaluate(ellc_handle* h, int32_t kf_slot, int32_t frame_slot, int32_
     CU_TRY(h, cudaMemcpyAsync(out, h->d_trace + (int64_t)level * ELLC_MAX_TRACE_ITERS, sizeof(ellc_iter_trace), cudaMemcpyDeviceToHost, h->stream));
     if (weight_image) CU_TRY(h, cudaMemcpyAsync(weight_image, h->d_weight, (size_t)npx * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(h, cudaStreamSynchronize(h->stream));
-    h->pin_used = 0;
     return ELLC_OK;
 }
 
@@ -867,15 +997,14 @@ int ellc_solve_update_rt(ellc_handle* h, const float H[36], const float b[6], co
     if (!h) return ELLC_ERR_INVALID;
     if (!H || !b || !pose_in || !pose_out || !delta || !weighted_pose) { h->err = "null argument"; return ELLC_ERR_INVALID; }
     CU_TRY(h, cudaSetDevice(h->cfg.device));
-    float in[54], outv[26];
+    float in[54], outv[27];
     for (int i = 0; i < 36; ++i) in[i] = H[i];
     for (int i = 0; i < 6; ++i) { in[36 + i] = b[i]; in[42 + i] = pose_in[i]; in[48 + i] = h->cfg.weight[i]; }
     int rc = stage_h2d(h, h->d_small, in, sizeof(in));
     if (rc) return rc;
-    h->launches += launch_solve_update(h->stream, h->d_small, h->d_small + 64);
+    h->launches += launch_solve_update(h->stream, h->d_small, h->d_small + 64, h->cfg.arithmetic == ELLC_ARITH_FAST ? 1 : 0);
     CU_TRY(h, cudaMemcpyAsync(outv, h->d_small + 64, sizeof(outv), cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(h, cudaStreamSynchronize(h->stream));
-    h->pin_used = 0;
     for (int i = 0; i < 6; ++i) { pose_out[i] = outv[i]; delta[i] = outv[6 + i]; }
     *weighted_pose = outv[12];
     if (rt_out) for (int i = 0; i < 12; ++i) rt_out[i] = outv[14 + i];
@@ -903,6 +1032,7 @@ int ellc_read_frame_level(ellc_handle* h, int32_t slot, int32_t level, uint8_t* 
     CU_TRY(h, cudaSetDevice(h->cfg.device));
     int rc = flush_dirty(h);
     if (rc) return rc;
+    { int rcw = main_waits_batches(h); if (rcw) return rcw; }
     const Geometry& g = h->geo;
     if (image) CU_TRY(h, cudaMemcpyAsync(image, h->fr_img + (int64_t)slot * g.img_off[kLevels] + g.img_off[level],
                                          (size_t)g.pyr_w[level] * g.pyr_h[level], cudaMemcpyDeviceToHost, h->stream));
@@ -914,7 +1044,6 @@ int ellc_read_frame_level(ellc_handle* h, int32_t slot, int32_t level, uint8_t* 
                                   cudaMemcpyDeviceToHost, h->stream));
     }
     CU_TRY(h, cudaStreamSynchronize(h->stream));
-    h->pin_used = 0;
     for (size_t i = 0; i < tex.size(); ++i) {           // unpack only: the differences were taken on the device
         if (gradx) gradx[i] = 0.5f * (float)tex_gx2(tex[i]);
         if (grady) grady[i] = 0.5f * (float)tex_gy2(tex[i]);
@@ -929,6 +1058,7 @@ int ellc_read_keyframe_level(ellc_handle* h, int32_t slot, int32_t level, uint8_
     CU_TRY(h, cudaSetDevice(h->cfg.device));
     int rc = flush_dirty(h);
     if (rc) return rc;
+    { int rcw = main_waits_batches(h); if (rcw) return rcw; }
     const Geometry& g = h->geo;
     if (image) CU_TRY(h, cudaMemcpyAsync(image, h->kf_img + (int64_t)slot * g.img_off[kLevels] + g.img_off[level],
                                          (size_t)g.pyr_w[level] * g.pyr_h[level], cudaMemcpyDeviceToHost, h->stream));
@@ -936,7 +1066,6 @@ int ellc_read_keyframe_level(ellc_handle* h, int32_t slot, int32_t level, uint8_
                                         (size_t)g.cols[level] * g.rows[level], cudaMemcpyDeviceToHost, h->stream));
     if (count) CU_TRY(h, cudaMemcpyAsync(count, h->kf_count + slot * kLevels + level, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(h, cudaStreamSynchronize(h->stream));
-    h->pin_used = 0;
     return ELLC_OK;
 }
 
@@ -947,6 +1076,19 @@ void ellc_se3_exp(const float pose[6], float T[16]) {
     pose_to_rt_f(pose, Rt);
     for (int i = 0; i < 12; ++i) T[i] = Rt[i];
     T[12] = T[13] = T[14] = 0.f; T[15] = 1.f;
+}
+
+// The FAST flavour's closed-form small-angle exponential / logarithm (ellc_lie.cuh), as host code for the CPU tests
+void ellc_se3_exp_closed(const float pose[6], float T[16]) {
+    float Rt[12];
+    se3_exp_small_f(pose, Rt);
+    for (int i = 0; i < 12; ++i) T[i] = Rt[i];
+    T[12] = T[13] = T[14] = 0.f; T[15] = 1.f;
+}
+int ellc_se3_log_closed(const float T[16], float pose[6]) {
+    float Rt[12];
+    for (int i = 0; i < 12; ++i) Rt[i] = T[i];
+    return se3_log_small_f(Rt, pose) ? 1 : 0;
 }
 
 int64_t ellc_launch_count(const ellc_handle* h) { return h ? h->launches : 0; }
@@ -965,6 +1107,7 @@ int ellc_reset_keyframe_weights(ellc_handle* h, int32_t kf_slot) {
     CU_TRY(h, cudaSetDevice(h->cfg.device));
     int rc = ensure_lc_pools(h);
     if (rc) return rc;
+    { int rcw = main_waits_batches(h); if (rcw) return rcw; }
     const int64_t win = h->geo.win_off[kLevels];
     CU_TRY(h, cudaMemsetAsync(h->kf_weight + kf_slot * win, 0, (size_t)win * sizeof(float), h->stream));
     for (int l = 0; l < kLevels; ++l) h->kf_wcount[(size_t)kf_slot * kLevels + l] = 0;
@@ -985,6 +1128,7 @@ int ellc_accumulate_weights(ellc_handle* h, int32_t kf_slot, int32_t n, const in
     if (rc) return rc;
     rc = flush_dirty(h);                                   // the keyframe's mask must be current
     if (rc) return rc;
+    { int rcw = main_waits_batches(h); if (rcw) return rcw; }
     rc = stage_h2d(h, h->d_slots, frame_slots, (size_t)n * sizeof(int));
     if (rc) return rc;
     const int64_t win = h->geo.win_off[kLevels];
@@ -1002,6 +1146,7 @@ int ellc_finalise_weights(ellc_handle* h, int32_t kf_slot) {
     CU_TRY(h, cudaSetDevice(h->cfg.device));
     rc = ensure_lc_pools(h);
     if (rc) return rc;
+    { int rcw = main_waits_batches(h); if (rcw) return rcw; }
     h->launches += launch_finalise_weights(h->stream, h->kf_weight + kf_slot * h->geo.win_off[kLevels], &h->kf_wcount[(size_t)kf_slot * kLevels], h->geo);
     CU_TRY(h, cudaGetLastError());
     h->kf_lc_ready[kf_slot] = 0;
@@ -1015,6 +1160,7 @@ int ellc_upload_keyframe_weights(ellc_handle* h, int32_t kf_slot, const float* c
     CU_TRY(h, cudaSetDevice(h->cfg.device));
     int rc = ensure_lc_pools(h);
     if (rc) return rc;
+    { int rcw = main_waits_batches(h); if (rcw) return rcw; }
     const int64_t win = h->geo.win_off[kLevels];
     for (int l = 0; l < kLevels; ++l) {
         const size_t bytes = (size_t)(h->geo.win_off[l + 1] - h->geo.win_off[l]) * sizeof(float);
@@ -1032,6 +1178,7 @@ int ellc_read_keyframe_weights(ellc_handle* h, int32_t kf_slot, int32_t level, f
     CU_TRY(h, cudaSetDevice(h->cfg.device));
     int rc = ensure_lc_pools(h);
     if (rc) return rc;
+    { int rcw = main_waits_batches(h); if (rcw) return rcw; }
     const size_t npx = (size_t)(h->geo.win_off[level + 1] - h->geo.win_off[level]);
     if (weight) CU_TRY(h, cudaMemcpyAsync(weight, h->kf_weight + kf_slot * h->geo.win_off[kLevels] + h->geo.win_off[level], npx * sizeof(float),
                                           cudaMemcpyDeviceToHost, h->stream));
@@ -1046,6 +1193,7 @@ int ellc_read_frame_weights(ellc_handle* h, int32_t frame_slot, int32_t level, f
     CU_TRY(h, cudaSetDevice(h->cfg.device));
     int rc = ensure_lc_pools(h);
     if (rc) return rc;
+    { int rcw = main_waits_batches(h); if (rcw) return rcw; }
     const size_t npx = (size_t)(h->geo.win_off[level + 1] - h->geo.win_off[level]);
     CU_TRY(h, cudaMemcpyAsync(weight, h->fr_weight + frame_slot * h->geo.win_off[kLevels] + h->geo.win_off[level], npx * sizeof(float),
                               cudaMemcpyDeviceToHost, h->stream));
@@ -1063,6 +1211,7 @@ int ellc_prepare_keyframes_lc(ellc_handle* h, int32_t n, const int32_t* kf_slots
     if (rc) return rc;
     rc = flush_dirty(h);                                   // selection lists of the current depth
     if (rc) return rc;
+    { int rcw = main_waits_batches(h); if (rcw) return rcw; }
     int* d_slots = h->d_slots + h->slots_cap;
     rc = stage_h2d(h, d_slots, kf_slots, (size_t)n * sizeof(int));
     if (rc) return rc;
@@ -1088,16 +1237,10 @@ int ellc_selftest_division(ellc_handle* h, int64_t n, uint64_t seed, int64_t mis
 }
 void* ellc_stream_of(ellc_handle* h, int32_t which) {
     if (!h) return nullptr;
-    return which == 1 ? (void*)h->copy_stream : which == 2 ? (void*)h->d2h_stream : (void*)h->stream;
+    return which == 1 ? (void*)h->copy_stream : which == 2 ? (void*)h->d2h_stream : which == 3 ? (void*)h->tstream[0]
+         : which == 4 ? (void*)h->tstream[1] : (void*)h->stream;
 }
-float ellc_last_track_kernel_ms(ellc_handle* h) {
-    if (!h || !h->ev_valid) return -1.f;
-    float ms = -1.f;
-    const int r = (int)(h->batch_seq & 3);
-    if (cudaEventSynchronize(h->ev1r[r]) != cudaSuccess) return -1.f;
-    if (cudaEventElapsedTime(&ms, h->ev0r[r], h->ev1r[r]) != cudaSuccess) return -1.f;
-    return ms;
-}
+float ellc_last_track_kernel_ms(ellc_handle* h) { return ellc_batch_kernel_ms(h, 0); }
 
 float ellc_batch_kernel_ms(ellc_handle* h, int32_t batches_ago) {
     if (!h || !h->ev_valid || batches_ago < 0 || batches_ago > 3 || h->batch_seq - batches_ago < 1) return -1.f;
@@ -1106,6 +1249,211 @@ float ellc_batch_kernel_ms(ellc_handle* h, int32_t batches_ago) {
     if (cudaEventSynchronize(h->ev1r[r]) != cudaSuccess) return -1.f;
     if (cudaEventElapsedTime(&ms, h->ev0r[r], h->ev1r[r]) != cudaSuccess) return -1.f;
     return ms;
+}
+
+float ellc_batch_interval_ms(ellc_handle* h, int32_t batches_ago) {
+    if (!h || !h->ev_valid || batches_ago < 0 || batches_ago > 2 || h->batch_seq - batches_ago < 2) return -1.f;
+    float ms = -1.f;
+    const int r = (int)((h->batch_seq - batches_ago) & 3), q = (int)((h->batch_seq - batches_ago - 1) & 3);
+    if (cudaEventSynchronize(h->ev1r[r]) != cudaSuccess) return -1.f;
+    if (cudaEventElapsedTime(&ms, h->ev1r[q], h->ev1r[r]) != cudaSuccess) return -1.f;
+    return ms;
+}
+
+}  // extern "C"
+
+// =====================================================================================================================
+// Multi-GPU result exchange
+// =====================================================================================================================
+static XchgHeader* xchg_header(const ellc_exchange* xc, int d) { return reinterpret_cast<XchgHeader*>(xc->peer_block[d]); }
+static ellc_result* xchg_table(const ellc_exchange* xc, int d, int r) {
+    return reinterpret_cast<ellc_result*>(reinterpret_cast<char*>(xc->peer_block[d]) + sizeof(XchgHeader)) + (size_t)r * xc->capacity;
+}
+static void exchange_release(ellc_handle* h) {
+    ellc_exchange* xc = h->xc;
+    if (!xc) return;
+    for (int d = 0; d < xc->world; ++d)
+        if (xc->peer_ipc[d] && xc->peer_block[d]) cudaIpcCloseMemHandle(xc->peer_block[d]);
+    cudaFree(xc->block);
+    cudaFree(xc->d_ctr);
+    if (xc->h_poll) cudaFreeHost(xc->h_poll);
+    delete xc;
+    h->xc = nullptr;
+}
+// one 8-byte read of a counter in this or a peer GPU's memory, through the download stream
+static int xchg_read_counter(ellc_handle* h, const unsigned long long* dev, unsigned long long* out) {
+    CU_TRY(h, cudaMemcpyAsync(h->xc->h_poll, dev, sizeof(unsigned long long), cudaMemcpyDefault, h->d2h_stream));
+    CU_TRY(h, cudaStreamSynchronize(h->d2h_stream));
+    *out = *h->xc->h_poll;
+    return ELLC_OK;
+}
+static int xchg_poll_until(ellc_handle* h, const unsigned long long* dev, unsigned long long want, double timeout_s, const char* what) {
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int spins = 0;; ++spins) {
+        unsigned long long v = 0;
+        int rc = xchg_read_counter(h, dev, &v);
+        if (rc) return rc;
+        if (v >= want) return ELLC_OK;
+        if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > timeout_s) {
+            h->err = std::string("result exchange timed out waiting for ") + what +
+                     " (every rank must call ellc_track_batch_exchange / ellc_exchange_wait for every token, in order)";
+            return ELLC_ERR_NOT_READY;
+        }
+        if (spins > 4) std::this_thread::sleep_for(std::chrono::microseconds(20));
+    }
+}
+static int xchg_finish_attach(ellc_handle* h) {
+    ellc_exchange* xc = h->xc;
+    std::vector<unsigned long long*> ptrs((size_t)kXchgRing * ELLC_MAX_RANKS, nullptr);
+    for (int r = 0; r < kXchgRing; ++r)
+        for (int d = 0; d < xc->world; ++d) ptrs[(size_t)r * ELLC_MAX_RANKS + d] = &xchg_header(xc, d)->arrived[r];
+    if (!xc->d_ctr) CU_TRY(h, cudaMalloc(&xc->d_ctr, ptrs.size() * sizeof(unsigned long long*)));
+    CU_TRY(h, cudaMemcpy(xc->d_ctr, ptrs.data(), ptrs.size() * sizeof(unsigned long long*), cudaMemcpyHostToDevice));
+    xc->attached = true;
+    return ELLC_OK;
+}
+
+extern "C" {
+
+int ellc_exchange_create(ellc_handle* h, int32_t rank, int32_t world, int32_t capacity, uint8_t ipc_handle[ELLC_IPC_HANDLE_BYTES]) {
+    if (!h) return ELLC_ERR_INVALID;
+    if (world < 1 || world > ELLC_MAX_RANKS || rank < 0 || rank >= world || capacity < 1) { h->err = "bad rank / world / capacity"; return ELLC_ERR_INVALID; }
+    if (h->xc) { h->err = "this handle already has an exchange"; return ELLC_ERR_INVALID; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == ELLC_IPC_HANDLE_BYTES, "ELLC_IPC_HANDLE_BYTES");
+    CU_TRY(h, cudaSetDevice(h->cfg.device));
+    ellc_exchange* xc = new (std::nothrow) ellc_exchange();
+    if (!xc) { h->err = "out of host memory"; return ELLC_ERR_INVALID; }
+    xc->rank = rank; xc->world = world; xc->capacity = capacity;
+    h->xc = xc;
+    const size_t bytes = sizeof(XchgHeader) + (size_t)kXchgRing * capacity * sizeof(ellc_result);
+    cudaError_t e = cudaMalloc(&xc->block, bytes);
+    if (e == cudaSuccess) e = cudaMemset(xc->block, 0, bytes);
+    if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&xc->h_poll), 64, cudaHostAllocDefault);
+    if (e != cudaSuccess) { h->err = std::string("exchange allocation: ") + cudaGetErrorString(e); exchange_release(h); return ELLC_ERR_CUDA; }
+    xc->peer_block[rank] = xc->block;
+    if (ipc_handle) {
+        cudaIpcMemHandle_t ih;
+        std::memset(&ih, 0, sizeof(ih));
+        e = cudaIpcGetMemHandle(&ih, xc->block);
+        if (e != cudaSuccess) {                            // same-process attachment (ellc_exchange_attach_local) still works
+            (void)cudaGetLastError();
+            std::memset(&ih, 0, sizeof(ih));
+            h->err = std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e);
+        }
+        std::memcpy(ipc_handle, &ih, sizeof(ih));
+    }
+    return ELLC_OK;
+}
+
+int ellc_exchange_attach_ipc(ellc_handle* h, const uint8_t* ipc_handles) {
+    if (!h) return ELLC_ERR_INVALID;
+    if (!h->xc || !ipc_handles) { h->err = "no exchange / null handles"; return ELLC_ERR_INVALID; }
+    ellc_exchange* xc = h->xc;
+    CU_TRY(h, cudaSetDevice(h->cfg.device));
+    for (int d = 0; d < xc->world; ++d) {
+        if (d == xc->rank || xc->peer_block[d]) continue;
+        cudaIpcMemHandle_t ih;
+        std::memcpy(&ih, ipc_handles + (size_t)d * ELLC_IPC_HANDLE_BYTES, sizeof(ih));
+        void* ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, ih, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            h->err = std::string("cudaIpcOpenMemHandle(rank ") + std::to_string(d) + "): " + cudaGetErrorString(e);
+            return ELLC_ERR_CUDA;
+        }
+        xc->peer_block[d] = ptr;
+        xc->peer_ipc[d] = true;
+    }
+    return xchg_finish_attach(h);
+}
+
+int ellc_exchange_attach_local(ellc_handle* h, ellc_handle* const* peers) {
+    if (!h) return ELLC_ERR_INVALID;
+    if (!h->xc || !peers) { h->err = "no exchange / null peer list"; return ELLC_ERR_INVALID; }
+    ellc_exchange* xc = h->xc;
+    CU_TRY(h, cudaSetDevice(h->cfg.device));
+    for (int d = 0; d < xc->world; ++d) {
+        if (d == xc->rank) continue;
+        ellc_handle* q = peers[d];
+        if (!q || !q->xc || q->xc->rank != d || q->xc->world != xc->world || q->xc->capacity != xc->capacity) {
+            h->err = "peer handle without a matching exchange (same world size and capacity, rank = its index)"; return ELLC_ERR_INVALID;
+        }
+        if (q->cfg.device != h->cfg.device) {
+            int can = 0;
+            CU_TRY(h, cudaDeviceCanAccessPeer(&can, h->cfg.device, q->cfg.device));
+            if (!can) { h->err = "no peer access between the two devices"; return ELLC_ERR_CUDA; }
+            cudaError_t e = cudaDeviceEnablePeerAccess(q->cfg.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { h->err = std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e); return ELLC_ERR_CUDA; }
+            (void)cudaGetLastError();
+        }
+        xc->peer_block[d] = q->xc->block;
+        xc->peer_ipc[d] = false;
+    }
+    return xchg_finish_attach(h);
+}
+
+int ellc_exchange_destroy(ellc_handle* h) {
+    if (!h) return ELLC_ERR_INVALID;
+    cudaSetDevice(h->cfg.device);
+    for (int i = 0; i < 2; ++i) cudaStreamSynchronize(h->tstream[i]);
+    cudaStreamSynchronize(h->d2h_stream);
+    exchange_release(h);
+    return ELLC_OK;
+}
+
+int ellc_track_batch_exchange(ellc_handle* h, int32_t n, const ellc_pair* pairs, const int32_t* global_index, int32_t n_total,
+                              int32_t root, int64_t* token) {
+    if (!h) return ELLC_ERR_INVALID;
+    ellc_exchange* xc = h->xc;
+    if (!xc || !xc->attached) { h->err = "no attached exchange: ellc_exchange_create + ellc_exchange_attach_* first"; return ELLC_ERR_NOT_READY; }
+    if (n < 0 || (n > 0 && (!pairs || !global_index)) || !token) { h->err = "bad exchange batch arguments"; return ELLC_ERR_INVALID; }
+    if (n_total < n || n_total > xc->capacity || root < -1 || root >= xc->world) { h->err = "n_total exceeds the exchange capacity / bad root"; return ELLC_ERR_INVALID; }
+    for (int i = 0; i < n; ++i)
+        if (global_index[i] < 0 || global_index[i] >= n_total) { h->err = "global pair index out of range"; return ELLC_ERR_INVALID; }
+    CU_TRY(h, cudaSetDevice(h->cfg.device));
+    const long long t = xc->token + 1;
+    const int r = (int)(t % kXchgRing);
+    XchgLaunch xl;
+    xl.global_index = global_index;
+    const int d0 = root < 0 ? 0 : root, d1 = root < 0 ? xc->world : root + 1;
+    for (int d = d0; d < d1; ++d) {
+        // flow control: receiver d has copied out the token that used this table last
+        if (t > kXchgRing) {
+            int rc = xchg_poll_until(h, &xchg_header(xc, d)->released[r], (unsigned long long)(t - kXchgRing), 20.0, "a receiver to release its table");
+            if (rc) return rc;
+        }
+        xl.dst[xl.n_dst++] = xchg_table(xc, d, r);
+    }
+    int rc = track_launch(h, n, pairs, false, &xl);
+    if (rc) return rc;
+    cudaStream_t ts = h->tstream[h->batch_seq & 1];
+    h->launches += launch_xchg_signal(ts, xc->d_ctr + (size_t)r * ELLC_MAX_RANKS + d0, d1 - d0, (unsigned long long)n);
+    CU_TRY(h, cudaGetLastError());
+    if (root < 0 || root == xc->rank) xc->expected[r] += (unsigned long long)n_total;
+    xc->tok[r].seq = h->batch_seq; xc->tok[r].n = n; xc->tok[r].n_total = n_total; xc->tok[r].root = root;
+    xc->token = t;
+    *token = t;
+    return ELLC_OK;
+}
+
+int ellc_exchange_wait(ellc_handle* h, int64_t token, ellc_result* results) {
+    if (!h) return ELLC_ERR_INVALID;
+    ellc_exchange* xc = h->xc;
+    if (!xc || !xc->attached) { h->err = "no attached exchange"; return ELLC_ERR_NOT_READY; }
+    if (token < 1 || token > xc->token || token + kXchgRing <= xc->token) { h->err = "unknown or expired exchange token"; return ELLC_ERR_INVALID; }
+    CU_TRY(h, cudaSetDevice(h->cfg.device));
+    const int r = (int)(token % kXchgRing);
+    const ellc_exchange::Tok tk = xc->tok[r];
+    CU_TRY(h, cudaEventSynchronize(h->batch_ev[tk.seq & 3]));                  // this rank's own batch
+    note_done(h, tk.seq);
+    if (tk.root >= 0 && tk.root != xc->rank) return ELLC_OK;                   // not a receiver of this token
+    int rc = xchg_poll_until(h, &xchg_header(xc, xc->rank)->arrived[r], xc->expected[r], 30.0, "the records of all ranks");
+    if (rc) return rc;
+    if (results) CU_TRY(h, cudaMemcpyAsync(results, xchg_table(xc, xc->rank, r), (size_t)tk.n_total * sizeof(ellc_result), cudaMemcpyDeviceToHost, h->d2h_stream));
+    h->launches += launch_xchg_store(h->d2h_stream, &xchg_header(xc, xc->rank)->released[r], (unsigned long long)token);
+    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaStreamSynchronize(h->d2h_stream));
+    return ELLC_OK;
 }
 
 }  // extern "C"

@@ -113,6 +113,12 @@ struct TrackParams {
     const uint32_t* lcp_pool;  // ... + the keyframe pixel as a texel word (2 gradx + 512 : 10 | 2 grady + 512 : 10 | - | I : 8): 20 B / pixel
     const float* lc_H;         // [kf_slot][kLevels][kLcHStride]: hessian (36, src/PixelWisePyramid.cpp:938), hessianInv (36, :939), ok (1)
     uint32_t zero_mask;        // always 0: an opaque zero the pixel loop uses to build ordering dependences
+    float lm_lambda, lm_up, lm_down;   // Levenberg-Marquardt damping (0 = plain Gauss-Newton, the reference) and its step-rejection factors
+    // multi-GPU result exchange (ellc_track_batch_exchange): besides `results`, the record of pair i is stored at
+    // xchg_dst[d][xchg_index[i]] for d < xchg_n -- result tables in the memory of this or of peer GPUs (NVLink stores)
+    int xchg_n;
+    ellc_result* xchg_dst[ELLC_MAX_RANKS];
+    const int* xchg_index;
 };
 
 }  // namespace ellc

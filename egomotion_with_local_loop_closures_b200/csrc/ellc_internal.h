@@ -38,13 +38,14 @@ int launch_pull_host(cudaStream_t st, void* dst, const void* src_host_devptr, si
 // Launches the GN tracking kernel for p.n_pairs pairs with `cluster` CTAs per pair.  Returns kernels launched (1) or a
 // negative value on launch-configuration failure (cudaGetLastError carries the reason).
 int launch_track(cudaStream_t st, const TrackParams& p, int cluster, bool strict);
-// warp-specialised forward kernel (8 pixel warps + 1 solver warp, two pairs per CTA in a ping-pong pipeline); large batches
-int launch_track_ws(cudaStream_t st, const TrackParams& p, bool strict);
 // loop-closure (inverse-compositional constant-weight) variant: one CTA per pair, pairs = p.order[0 .. p.n_pairs)
 int launch_track_lc(cudaStream_t st, const TrackParams& p, bool strict);
+// result exchange: thread d adds n_records to *d_counters[d] (system scope); store a value to a counter (system scope)
+int launch_xchg_signal(cudaStream_t st, unsigned long long* const* d_counters, int n_dst, unsigned long long n_records);
+int launch_xchg_store(cudaStream_t st, unsigned long long* d_counter, unsigned long long value);
 // single-thread kernel running solve_update_f on the device (ellc_solve_update)
 // div2_rn_shared (the pixel loop's shared-reciprocal exact division) against __fdiv_rn on n pseudo-random operand triples
 int launch_div_selftest(cudaStream_t st, long long n, unsigned long long seed, unsigned long long* d_counts /*[2]*/);
-int launch_solve_update(cudaStream_t st, const float* d_in /*H36 b6 pose6 weight6*/, float* d_out /*pose6 delta6 wp1 ok1*/);
+int launch_solve_update(cudaStream_t st, const float* d_in /*H36 b6 pose6 weight6*/, float* d_out /*pose6 delta6 wp1 ok1 rt12 small1*/, int fast);
 
 }  // namespace ellc

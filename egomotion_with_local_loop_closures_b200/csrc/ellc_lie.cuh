@@ -353,6 +353,87 @@ __host__ __device__ inline bool solve_update_f(const float (&H)[36], const float
 }
 
 
+// ---- closed-form SE(3) exp / log for small rotations (FAST flavour of K5) -------------------------------------------------
+// SURVEY 8a row I allows a closed-form replacement of Eigen's Pade exponential / Schur logarithm ("agrees to ~1e-6").  The FAST
+// flavour of K5 uses these when every rotation involved is below kSmallTheta2 = 0.04 rad^2 (11.5 degrees: every pose a
+// frame-to-keyframe track produces); anything larger takes the op-for-op Pade path, as does the STRICT flavour always.
+// fp32 throughout, power series in theta^2 (truncation < 1e-10 at the bound), ~60 instructions each, no divisions:
+// the Pade path costs ~700 per exponential even lane-distributed, and its 4x4 LU is a chain of 7 dependent divisions.
+// Measured against the Pade / double-log path (tests/test_oracle_known_answers.py): entries of exp within 2.5e-7, log within 2e-7.
+constexpr float kSmallTheta2 = 0.04f;
+
+// exp(hat(p)), rows 0..2 (SE3_vec layout r11 r12 r13 t1 r21 ..., src/PixelWisePyramid.cpp:162-173); requires |omega|^2 < ~0.1
+__host__ __device__ inline void se3_exp_small_f(const float p[6], float (&Rt)[12]) {
+    const float wx = p[0], wy = p[1], wz = p[2], vx = p[3], vy = p[4], vz = p[5];
+    const float t2 = wx * wx + wy * wy + wz * wz;
+    // A = sin(t)/t, B = (1 - cos t)/t^2, C = (t - sin t)/t^3
+    const float A = 1.0f - t2 * (1.0f / 6.0f) * (1.0f - t2 * (1.0f / 20.0f) * (1.0f - t2 * (1.0f / 42.0f) * (1.0f - t2 * (1.0f / 72.0f))));
+    const float B = 0.5f * (1.0f - t2 * (1.0f / 12.0f) * (1.0f - t2 * (1.0f / 30.0f) * (1.0f - t2 * (1.0f / 56.0f) * (1.0f - t2 * (1.0f / 90.0f)))));
+    const float C = (1.0f / 6.0f) * (1.0f - t2 * (1.0f / 20.0f) * (1.0f - t2 * (1.0f / 42.0f) * (1.0f - t2 * (1.0f / 72.0f) * (1.0f - t2 * (1.0f / 110.0f)))));
+    // R = I + A W + B W^2, W^2 = w w^T - t2 I
+    const float Bx = B * wx, By = B * wy, Bz = B * wz;
+    const float d = 1.0f - B * t2;
+    Rt[0] = d + Bx * wx;            Rt[1] = Bx * wy - A * wz;       Rt[2] = Bx * wz + A * wy;
+    Rt[4] = Bx * wy + A * wz;       Rt[5] = d + By * wy;            Rt[6] = By * wz - A * wx;
+    Rt[8] = Bx * wz - A * wy;       Rt[9] = By * wz + A * wx;       Rt[10] = d + Bz * wz;
+    // t = V v, V = I + B W + C W^2:  v + B (w x v) + C (w x (w x v))
+    const float cx = wy * vz - wz * vy, cy = wz * vx - wx * vz, cz = wx * vy - wy * vx;
+    const float ex = wy * cz - wz * cy, ey = wz * cx - wx * cz, ez = wx * cy - wy * cx;
+    Rt[3] = vx + B * cx + C * ex;
+    Rt[7] = vy + B * cy + C * ey;
+    Rt[11] = vz + B * cz + C * ez;
+}
+
+// log of the rigid transform in rows 0..2 of Rt -> pose, entry extraction as src/Frame.cpp:523-528.  Returns false (pose
+// untouched) when the rotation is not small (sin^2 theta >= kSmallTheta2 or cos theta <= 0.9): the caller then takes the
+// general path.  theta / sin(theta) from the arcsine series in sin^2 theta (of the antisymmetric part, exact differences for
+// small rotations), V^-1 = I - W/2 + coef W^2 with coef = (1 - theta sin theta / (2 (1 - cos theta))) / theta^2 as a series.
+__host__ __device__ inline bool se3_log_small_f(const float (&Rt)[12], float pose[6]) {
+    const float ax = 0.5f * (Rt[9] - Rt[6]), ay = 0.5f * (Rt[2] - Rt[8]), az = 0.5f * (Rt[4] - Rt[1]);   // sin(theta) n
+    const float s2 = ax * ax + ay * ay + az * az;
+    const float c = 0.5f * (Rt[0] + Rt[5] + Rt[10] - 1.0f);
+    if (!(s2 < kSmallTheta2 && c > 0.9f)) return false;
+    // asin(s)/s = 1 + s2/6 + 3 s2^2/40 + 15 s2^3/336 + 105 s2^4/3456 + 945 s2^5/42240 + 10395 s2^6/599040
+    const float k = 1.0f + s2 * (1.0f / 6.0f + s2 * (3.0f / 40.0f + s2 * (15.0f / 336.0f + s2 * (105.0f / 3456.0f +
+                    s2 * (945.0f / 42240.0f + s2 * (10395.0f / 599040.0f))))));
+    const float wx = k * ax, wy = k * ay, wz = k * az;
+    const float t2 = (k * k) * s2;
+    const float coef = 1.0f / 12.0f + t2 * (1.0f / 720.0f + t2 * (1.0f / 30240.0f + t2 * (1.0f / 1209600.0f)));
+    const float tx = Rt[3], ty = Rt[7], tz = Rt[11];
+    const float cx = wy * tz - wz * ty, cy = wz * tx - wx * tz, cz = wx * ty - wy * tx;
+    const float ex = wy * cz - wz * cy, ey = wz * cx - wx * cz, ez = wx * cy - wy * cx;
+    pose[0] = wx; pose[1] = wy; pose[2] = wz;
+    pose[3] = tx - 0.5f * cx + coef * ex;
+    pose[4] = ty - 0.5f * cy + coef * ey;
+    pose[5] = tz - 0.5f * cz + coef * ez;
+    return true;
+}
+
+// pose <- log(exp(delta) exp(pose)) with Rt = exp(hat(pose)) given and exp(hat(new pose)) returned: the FAST flavour's form of
+// src/PixelWisePyramid.cpp:484 + :153-173.  Returns false (nothing written) when a rotation is too large for the series.
+__host__ __device__ inline bool pose_update_small_f(const float (&delta)[6], const float (&Rt)[12], float (&pose)[6], float (&Rt_new)[12]) {
+    const float td = delta[0] * delta[0] + delta[1] * delta[1] + delta[2] * delta[2];
+    const float tp = pose[0] * pose[0] + pose[1] * pose[1] + pose[2] * pose[2];
+    if (!(td < kSmallTheta2 && tp < kSmallTheta2)) return false;
+    float E[12], T[12];
+    se3_exp_small_f(delta, E);
+    ELLC_UNROLL
+    for (int i = 0; i < 3; ++i) {
+        ELLC_UNROLL
+        for (int j = 0; j < 4; ++j) {
+            float s = E[4 * i] * Rt[j] + E[4 * i + 1] * Rt[4 + j] + E[4 * i + 2] * Rt[8 + j];
+            if (j == 3) s += E[4 * i + 3];
+            T[4 * i + j] = s;
+        }
+    }
+    float np[6];
+    if (!se3_log_small_f(T, np)) return false;
+    ELLC_UNROLL
+    for (int i = 0; i < 6; ++i) pose[i] = np[i];
+    se3_exp_small_f(np, Rt_new);
+    return true;
+}
+
 #ifdef __CUDACC__
 // ---- warp-cooperative K5 (device only) -------------------------------------------------------------------------------
 // The same LU as invert6_lu_f, with the six right-hand-side columns of [A | I] spread over lanes (lane % 6 owns one column
@@ -527,9 +608,9 @@ static __device__ __noinline__ float se3_exp_pade_warp(float p0, float p1, float
 // weighted_pose).  The 4x4 part runs lane-distributed: rt_pose_e is entry (lane & 15) of exp(hat(pose)) as computed for the
 // current iteration (rows 0..2 from Rt, row 3 exactly [0 0 0 1]), and *rt_new_e returns the same entry of exp(hat(new pose)) for
 // the next iteration (src/PixelWisePyramid.cpp:153-173), so only exp(delta) and exp(new pose) are evaluated.
-// updatePose() given column (lane % 6) of hessianInv in col[0..5] (all zeros for a singular hessian)
-__device__ inline void update_from_inverse_warp(const float (&col)[6], const float (&b)[6], const float (&weight)[6], float rt_pose_e,
-                                                float (&pose)[6], float (&delta)[6], float* weighted_pose, float* rt_new_e, int lane) {
+// deltapose and weightedPose (:466-479) given column (lane % 6) of hessianInv in col[0..5] (all zeros for a singular hessian)
+__device__ inline void delta_from_inverse_warp(const float (&col)[6], const float (&b)[6], const float (&weight)[6],
+                                               float (&delta)[6], float* weighted_pose, int lane) {
     // delta_i = -(sum_k Hinv[i][k] b[k]): lane k (< 6) holds Hinv[.][k]; products are exact in double, the sum runs k = 0..5
     const double bk = (double)b[lane % 6];
     ELLC_UNROLL
@@ -544,6 +625,9 @@ __device__ inline void update_from_inverse_warp(const float (&col)[6], const flo
     ELLC_UNROLL
     for (int i = 1; i < 6; ++i) wp = ELLC_ADD(wp, fabsf(ELLC_MUL(delta[i], weight[i])));
     *weighted_pose = wp;
+}
+// pose <- log(exp(delta) exp(pose)) (:484) with the reference's Pade exponentials, lane-distributed
+__device__ inline void pose_update_pade_warp(const float (&delta)[6], float rt_pose_e, float (&pose)[6], float* rt_new_e, int lane) {
     const int e = lane & 15;
     const float Ta = se3_exp_pade_warp(delta[0], delta[1], delta[2], delta[3], delta[4], delta[5], e);
     const float Te = m4w_mul(Ta, rt_pose_e, e);
@@ -553,6 +637,12 @@ __device__ inline void update_from_inverse_warp(const float (&col)[6], const flo
     T[12] = T[13] = T[14] = 0.f; T[15] = 1.f;                  // not read by the logarithm
     m4_log_f(T, pose);
     *rt_new_e = se3_exp_pade_warp(pose[0], pose[1], pose[2], pose[3], pose[4], pose[5], e);
+}
+// updatePose() given column (lane % 6) of hessianInv in col[0..5]
+__device__ inline void update_from_inverse_warp(const float (&col)[6], const float (&b)[6], const float (&weight)[6], float rt_pose_e,
+                                                float (&pose)[6], float (&delta)[6], float* weighted_pose, float* rt_new_e, int lane) {
+    delta_from_inverse_warp(col, b, weight, delta, weighted_pose, lane);
+    pose_update_pade_warp(delta, rt_pose_e, pose, rt_new_e, lane);
 }
 __device__ inline bool solve_update_warp(const float (&H)[36], const float (&b)[6], const float (&weight)[6], float rt_pose_e,
                                          float (&pose)[6], float (&delta)[6], float* weighted_pose, float* rt_new_e, int lane) {

@@ -31,6 +31,8 @@ extern "C" {
 
 #define ELLC_LEVELS 4                 /* util::MAX_PYRAMID_LEVEL, src/ExternVariable.h:40 */
 #define ELLC_MAX_TRACE_ITERS 16       /* per level; the reference's largest MAX_ITER is 12 (src/main.cpp:34) */
+#define ELLC_MAX_RANKS 8              /* GPUs of one NVSwitch box taking part in a result exchange                  */
+#define ELLC_IPC_HANDLE_BYTES 64      /* sizeof(cudaIpcMemHandle_t)                                                  */
 
 typedef enum ellc_status {
     ELLC_OK = 0,
@@ -69,6 +71,14 @@ typedef struct ellc_config {
     int32_t device;                   /* CUDA device ordinal                                                      */
     int32_t pairs_per_cta;            /* pairs one CTA tracks in lockstep (their serial solves overlap): 1..4;
                                          0 = choose from batch size.  Only used when ctas_per_pair resolves to 1  */
+    /* Levenberg-Marquardt damping of the on-device 6x6 solve (north_star).  The reference takes the plain Gauss-Newton step
+       unconditionally (hessianInv = hessian.inv(); updatePose(); src/PixelWisePyramid.cpp:451-453): lm_lambda = 0, the default,
+       is exactly that, bit for bit.  lm_lambda > 0: solve (H + lambda diag(H)) delta = -b; a step after which the mean weighted
+       squared residual rises is rejected on the device (pose restored, lambda *= lm_up, the step retaken and counted as an
+       iteration, result status bit 1), an accepted step multiplies lambda by lm_down.  Forward (Huber-reweighted) pairs only. */
+    float   lm_lambda;                /* initial damping per level; 0 = off                                       */
+    float   lm_up;                    /* > 1; 0 selects 4                                                         */
+    float   lm_down;                  /* in (0, 1]; 0 selects 0.5                                                 */
 } ellc_config;
 
 /* One frame-keyframe pair = one call of GetImagePoseEstimate (src/ImageFunc.h:31). */
@@ -90,7 +100,8 @@ typedef struct ellc_result {
     float   res_last[ELLC_LEVELS];    /* same at the level's last executed iteration (before its update)         */
     float   weighted_pose[ELLC_LEVELS]; /* PixelWisePyramid::weightedPose after the level's last update          */
     int32_t n_oob[ELLC_LEVELS];       /* selected pixels warped fully out of bounds at the last iteration         */
-    int32_t status;                   /* 0 ok; bit0: a singular hessian was met (zero step, as the reference)     */
+    int32_t status;                   /* 0 ok; bit0: a singular hessian was met (zero step, as the reference);
+                                         bit1: a Levenberg-Marquardt step was rejected (lm_lambda > 0 only)       */
     int32_t reserved[6];
 } ellc_result;                        /* 64 x 4 B */
 
@@ -105,7 +116,9 @@ typedef struct ellc_iter_trace {
     float   weight_sum;               /* sum w                                                                    */
     int32_t n_oob;
     int32_t executed;                 /* 1 if this iteration ran                                                  */
-    int32_t pad[5];
+    float   lm_lambda;                /* damping used by this iteration's solve (0 = plain Gauss-Newton)          */
+    int32_t lm_rejected;              /* 1: the residual rose, the previous linearisation point was restored      */
+    int32_t pad[3];
 } ellc_iter_trace;                    /* 64 x 4 B */
 
 /* Loop-closure candidate gating (globalOptimize::findMatch, src/GlobalOptimize.cpp:274-452). */
@@ -138,8 +151,10 @@ const char* ellc_version(void);
  * ellc_upload_keyframe additionally takes the depth / variance pyramids the depth module hands over
  *                      (frame::depth_pyramid[l], depthMap::depthvararrptr[l]; src/DepthPropagation.h:65-78) and runs
  *                      calculateNonZeroDepthPts() (src/Frame.cpp:295-301) for every level.
- * Both are asynchronous on the handle's stream; host buffers must stay valid until ellc_synchronize or the next
- * synchronous call (pinned memory recommended). */
+ * Both are asynchronous on the handle's COPY stream (they overlap the kernels of a batch in flight; writes to a slot that a
+ * batch still reads are ordered behind it automatically); host buffers must stay valid until ellc_synchronize or until the
+ * records of a batch launched after the upload have been fetched (pinned memory recommended).  Every consumer (track,
+ * ellc_prepare_*, evaluate, read-back) waits for pending uploads on its own stream. */
 int ellc_upload_frame(ellc_handle* h, int32_t frame_slot, const uint8_t* image);
 int ellc_upload_keyframe(ellc_handle* h, int32_t kf_slot, const uint8_t* image,
                          const float* const depth[ELLC_LEVELS], const float* const var[ELLC_LEVELS]);
@@ -190,8 +205,8 @@ int ellc_prepare_async(ellc_handle* h, int32_t n_frames, const int32_t* frame_sl
  * n * ELLC_LEVELS * ELLC_MAX_TRACE_ITERS records indexed [pair][level][iter]. */
 int ellc_track_batch(ellc_handle* h, int32_t n, const ellc_pair* pairs, ellc_result* results, ellc_iter_trace* trace);
 
-/* Same, asynchronous: only enqueues.  Results stay on the device in one of two alternating buffers: the returned pointer
- * stays valid until the second-next track call on this handle.  Uploads run on their own copy stream, so the uploads of
+/* Same, asynchronous: only enqueues.  Results stay on the device in a ring of four buffers: the returned pointer
+ * stays valid until three more track calls have been made on this handle.  Uploads run on their own copy stream, so the uploads of
  * the next batch overlap this batch's kernels as long as they go to slots this batch does not read (slot reuse is
  * detected and ordered automatically). */
 int ellc_track_batch_async(ellc_handle* h, int32_t n, const ellc_pair* pairs, const ellc_result** device_results);
@@ -199,6 +214,37 @@ int ellc_track_batch_async(ellc_handle* h, int32_t n, const ellc_pair* pairs, co
  * behind batches enqueued later). */
 int ellc_results_download(ellc_handle* h, const ellc_result* device_results, int32_t n, ellc_result* results);
 int ellc_synchronize(ellc_handle* h);
+/* Batches run on two internal tracking streams (consecutive batches overlap at their tails).  ellc_fence makes the stream
+ * returned by ellc_stream() wait for every batch enqueued so far, so that an event recorded there afterwards covers them. */
+int ellc_fence(ellc_handle* h);
+
+/* ---- multi-GPU: sharded batches with an in-kernel result exchange over NVLink peer memory -----------------------
+ * Frame-keyframe pairs are independent (each is one call of GetImagePoseEstimate, src/ImageFunc.cpp:49-315; the loop-closure thread
+ * issues them per keyframe, src/GlobalOptimize.cpp:480-610), so a pair list is sharded over the GPUs of one box with no data-path
+ * collective; the only exchange is the gather of the 256-byte ellc_result records (pose, hessian, counters) the host writes to
+ * poses_orig.txt / matchframes*.txt (src/main.cpp:373,382).  Here the gather is part of the tracking kernel: every rank owns a ring
+ * of result tables in its device memory, maps the tables of its peers (CUDA IPC between processes, peer access inside one process),
+ * and the kernel's epilogue stores each record at its GLOBAL pair index straight into the table of every receiving rank -- no NCCL
+ * call, no staging copy; a one-warp kernel behind it bumps the receivers' arrival counters.
+ *   ellc_exchange_create        allocate this rank's tables (`capacity` records each) and return the IPC handle of the block
+ *   ellc_exchange_attach_ipc    map the blocks of all ranks from their IPC handles (world x ELLC_IPC_HANDLE_BYTES bytes, rank order;
+ *                               the handles travel by any host channel: MPI, torch.distributed, a pipe, ...)
+ *   ellc_exchange_attach_local  the same for `world` handles living in THIS process (one host thread per GPU, or several handles on
+ *                               one GPU): peers[d] is the handle of rank d
+ *   ellc_track_batch_exchange   ellc_track_batch_async + exchange: global_index[i] in [0, n_total) is the position of pairs[i] in the
+ *                               global pair list; root = -1: every rank receives all records (all-gather), root >= 0: only that rank
+ *                               (gather).  Every rank calls it once per global batch with the same n_total and root; *token numbers
+ *                               the batch (the same on every rank).
+ *   ellc_exchange_wait          wait for this rank's batch and -- on a receiving rank -- for the records of ALL ranks, and copy the
+ *                               n_total records (global order) to `results` (HOST; may be NULL).  Every rank calls it for every token,
+ *                               in order; at most 3 tokens may be outstanding. */
+int ellc_exchange_create(ellc_handle* h, int32_t rank, int32_t world, int32_t capacity, uint8_t ipc_handle[ELLC_IPC_HANDLE_BYTES]);
+int ellc_exchange_attach_ipc(ellc_handle* h, const uint8_t* ipc_handles);
+int ellc_exchange_attach_local(ellc_handle* h, ellc_handle* const* peers);
+int ellc_track_batch_exchange(ellc_handle* h, int32_t n, const ellc_pair* pairs, const int32_t* global_index, int32_t n_total,
+                              int32_t root, int64_t* token);
+int ellc_exchange_wait(ellc_handle* h, int64_t token, ellc_result* results);
+int ellc_exchange_destroy(ellc_handle* h);
 
 /* ---- constant-weight loop-closure variant (src/PixelWisePyramid.cpp:500-974) --------------------------------------------------
  * Reference flow with util::FLAG_DO_CONST_WEIGHT_POSE_ESTIMATION: every sequential track of a frame on its keyframe ends each
@@ -252,6 +298,13 @@ void ellc_concat_origin(const float a[6], const float b[6], float dest[6]);
 /* exp(hat(pose)) as 4x4 row-major (src/Frame.cpp:443-471 calculateRandT) */
 void ellc_se3_exp(const float pose[6], float T[16]);
 
+/* The closed-form small-rotation exponential / logarithm the FAST flavour of the on-device pose update uses in place of Eigen's
+ * Pade .exp() / Schur .log() (src/Frame.cpp:511-521) when every rotation is below 11.5 degrees; host code,
+ * exported so that the CPU tests can pin them against the Pade / double-logarithm path.  ellc_se3_log_closed returns 1, or 0
+ * (pose untouched) when the rotation is outside the small-angle range. */
+void ellc_se3_exp_closed(const float pose[6], float T[16]);
+int  ellc_se3_log_closed(const float T[16], float pose[6]);
+
 /* ---- introspection for bench.py ----------------------------------------------------------------------------------- */
 /* kernels launched by this handle since creation (or since the last reset) */
 int64_t ellc_launch_count(const ellc_handle* h);
@@ -262,12 +315,17 @@ void*   ellc_stream(ellc_handle* h);
  * src/PixelWisePyramid.cpp:250-251) against __fdiv_rn on n pseudo-random operand triples; mismatches[0]: quotients with a normal
  * result that differ, mismatches[1]: differing quotients below 2^-120. */
 int ellc_selftest_division(ellc_handle* h, int64_t n, uint64_t seed, int64_t mismatches[2]);
-/* which: 0 = compute stream (same as ellc_stream), 1 = H2D upload stream, 2 = D2H result stream (diagnostics). */
+/* which: 0 = main compute stream (same as ellc_stream), 1 = H2D upload stream, 2 = D2H result stream, 3 / 4 = the two tracking streams (diagnostics). */
 void*   ellc_stream_of(ellc_handle* h, int32_t which);
 /* device time of the track kernel(s) of the most recent ellc_track_batch* call, in milliseconds (CUDA events) */
 float   ellc_last_track_kernel_ms(ellc_handle* h);
-/* the same for an earlier batch: batches_ago = 0 is the most recent ellc_track_batch* call, up to 3 */
+/* the same for an earlier batch: batches_ago = 0 is the most recent ellc_track_batch* call, up to 3.  Measured from the moment the
+ * batch's stream reaches the kernel to its completion: when batches are pipelined it INCLUDES the time the kernel's CTAs wait for
+ * the previous batch to leave the SMs. */
 float   ellc_batch_kernel_ms(ellc_handle* h, int32_t batches_ago);
+/* completion-to-completion interval between that batch's tracking kernel and the previous batch's: in a pipelined loop the average
+ * time a launch occupies the GPU (an upper bound of its exclusive kernel time) */
+float   ellc_batch_interval_ms(ellc_handle* h, int32_t batches_ago);
 
 #ifdef __cplusplus
 }

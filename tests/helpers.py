@@ -42,3 +42,29 @@ def full_H(h21):
 def rel_err(a, b):
     a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+# ---- measured-deviation log ----------------------------------------------------------------------------------------------
+# The GPU parity tests append what they MEASURED (worst deviation per quantity) to gpurun_out/parity_metrics.jsonl when that
+# directory exists, so that the tolerances written in the tests can be read next to the numbers a run actually produced
+# (DESIGN.md section 2 quotes them).
+def record(name, value, **extra):
+    import json
+    import os
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if not os.path.isdir(d):
+        return
+    row = dict(name=name, value=float(value), **extra)
+    with open(os.path.join(d, "parity_metrics.jsonl"), "a") as f:
+        f.write(json.dumps(row) + "\n")
+
+
+def iters_match(got, want, arith):
+    """Executed GN iterations per level.  STRICT runs the reference's Pade exponential / logarithm in K5: identical counts.  FAST
+    uses the closed-form small-angle exp / log there (allowed, +-1 iteration tolerated): a pose that differs
+    in the 7th digit can move weightedPose across the stop threshold one iteration earlier or later."""
+    got = [int(v) for v in got]
+    want = [int(v) for v in want]
+    if arith == 1:
+        return got == want
+    return all(abs(a - b) <= 1 for a, b in zip(got, want))

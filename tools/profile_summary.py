@@ -2,7 +2,7 @@
 
     python tools/profile_summary.py kernel <rep.ncu-rep> "<title>" "<command>"     -> markdown table on stdout
     python tools/profile_summary.py launches <launches.csv> "<command>"             -> markdown table on stdout
-    python tools/profile_summary.py traffic <rep.ncu-rep> <pairs> "<command>"       -> json on stdout (bench.py reads it)
+    python tools/profile_summary.py traffic <rep.ncu-rep> <pairs> "<command>" [version]  -> json on stdout (bench.py reads it)
 """
 import collections
 import csv
@@ -73,7 +73,18 @@ def main():
         val, unit = raw(rep)
         rd = to_bytes(val["dram__bytes_read.sum"], unit["dram__bytes_read.sum"])
         wr = to_bytes(val["dram__bytes_write.sum"], unit["dram__bytes_write.sum"])
-        print(json.dumps({"kernel": "gn_track_kernel", "pairs_per_launch": pairs, "dram_bytes_read": rd, "dram_bytes_write": wr,
+        # the library the capture ran with: the box's copy of the repo is this tree (gpurun snapshots it), so the version string of
+        # the in-tree library -- a hash of the kernel sources -- identifies it; bench.py refuses a capture of another build
+        import ctypes
+        import os
+        lib = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "egomotion_with_local_loop_closures_b200", "libellc_gn.so")
+        L = ctypes.CDLL(lib)
+        L.ellc_version.restype = ctypes.c_char_p
+        version = sys.argv[5] if len(sys.argv) > 5 else L.ellc_version().decode()
+        print(json.dumps({"kernel": "gn_track_kernel", "library_version": version, "workload": "pair_sweep_640x480",
+                          "pairs_per_launch": pairs, "dram_bytes_read": rd, "dram_bytes_write": wr,
+                          "inst_executed": float(val["smsp__inst_executed.sum"]),
+                          "issue_active_pct": float(val["smsp__issue_active.avg.pct_of_peak_sustained_active"]),
                           "kernel_ms_under_ncu": float(val["gpu__time_duration.sum"]), "l2_hit_rate_pct": float(val["lts__t_sector_hit_rate.pct"]),
                           "command": cmd, "report": rep.split("/")[-1]}, indent=1))
 
