@@ -507,10 +507,12 @@ def main():
     # the records of step k are fetched while step k+1 runs.  Every step still does all of its own work.
     pipe = {"k": 0, "pending": None, "last": None, "launched": 0}
 
+    overlap = os.environ.get("ELLC_OVERLAP") == "1"           # experiment: consecutive batches not serialised (measured slower)
+
     def note_kernel_time():
-        # completion-to-completion interval of consecutive tracking kernels: in the pipelined loop (two tracking streams, the head
-        # of batch k+1 fills the tail of batch k) this is the time one launch occupies the GPU -- an upper bound of its exclusive time
-        ms = trk.batch_interval_ms(1)
+        # CUDA events around the tracking kernel of the batch just fetched, on its own stream.  (With ELLC_OVERLAP=1 the kernels of
+        # consecutive batches run concurrently: then the completion-to-completion interval is the time a launch occupies the GPU.)
+        ms = trk.batch_interval_ms(1) if overlap else trk.batch_kernel_ms(1)
         if ms > 0:
             kernel_ms.append(ms)
 
@@ -529,7 +531,7 @@ def main():
             pipe["host_launch_ms"] = pipe.get("host_launch_ms", 0.0) + 1e3 * (time.perf_counter() - t1)
         if pipe["pending"] is not None:
             pipe["last"] = fetch(pipe["pending"])
-            if not e2e and pipe["launched"] >= 3:
+            if not e2e and pipe["launched"] >= (3 if overlap else 2):
                 note_kernel_time()
         pipe["pending"] = ticket
         pipe["k"] += 1
@@ -656,9 +658,9 @@ def main():
                 "traffic_unit": "bytes per launch (compare with algorithmic_bytes_per_launch)", "traffic_source": traffic_src,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                 "kernel": "gn_track_lc_kernel + gn_track_kernel" if lc else "gn_track_kernel", "kernel_ms_per_launch": k_ms,
-                "kernel_ms_definition": ("completion-to-completion interval of consecutive tracking kernels (CUDA events on the tracking streams): consecutive "
-                                         "batches overlap at their tails, so this is the time one launch occupies the GPU, an upper bound of its exclusive time"
-                                         if pipelined else "CUDA events around the tracking kernel(s) on their stream"),
+                "kernel_ms_definition": ("completion-to-completion interval of consecutive tracking kernels (ELLC_OVERLAP=1: batches run concurrently)"
+                                         if (pipelined and overlap) else "CUDA events around the tracking kernel(s) of a batch on the stream they are launched on, "
+                                         "inside the timed loop (the next step's preparation kernels share the GPU with its last wave)"),
                 "algorithmic_bytes_per_launch": alg, "pixel_iterations_per_launch": pix_it,
                 "kernel_share_of_step": k_ms / (ms / args.steps),
                 "mean_iters_per_level": [float(x) for x in res["n_iters"].mean(axis=0)],
@@ -718,8 +720,7 @@ def main():
                            "frames_per_gpu": args.frames, "pairs_per_gpu_per_step": n_pairs, "pairs_per_frame": args.pairs_per_frame,
                            "arithmetic": args.arith, "library": lib_version,
                            "pipelining": ("resident inputs held twice; steps alternate between the two sets of slots: preparation of step k+1 on a "
-                                          "low-priority stream overlaps the tracking kernel of step k, consecutive tracking kernels run on two streams "
-                                          "(the head of batch k+1 fills the tail of batch k), records of step k fetched during step k+1" if pipelined else
+                                          "low-priority stream overlaps the tracking kernel of step k, records of step k fetched during step k+1" if pipelined else
                                           "none (one set of slots; every step prepares, tracks and reads back before the next one starts)"),
                            "parallelism": f"pair list sharded by connected components (sequence segments) x{world}; gather: {gather_desc}",
                            "l2": "inputs (%.0f MB per step per GPU) exceed the 126 MB L2; no flush" % (h2d_bytes / 1e6) if h2d_bytes > 126e6 else

@@ -58,9 +58,10 @@ struct ellc_handle {
     LevelK K[kLevels];
     int rows_total;
     cudaStream_t stream;                               // main compute stream: prepare kernels, evaluate, read-backs, small staging copies
-    cudaStream_t tstream[2];                           // tracking kernels: batch `seq` runs on tstream[seq & 1], so that the first CTAs of
-                                                       // batch k+1 fill the SMs the last wave of batch k leaves idle (the work distributor
-                                                       // dispatches the older kernel's CTAs first); both at the highest priority
+    cudaStream_t tstream[2];                           // tracking kernels: batch `seq` runs on tstream[seq & 1], ordered behind batch seq - 1
+                                                       // by its completion event (or not, ELLC_OVERLAP=1: measured slower, see ellc_create);
+                                                       // both at the highest priority.  Keeping the batches off the main stream lets
+                                                       // synchronous main-stream calls (evaluate, read-backs) be ordered explicitly
     cudaEvent_t main_ev;                               // recorded on the main stream at every batch launch; the batch's stream waits for it
     cudaEvent_t hyp_ev; bool hyp_pending;              // depth pyramids built from hypotheses on the main stream (prep stream must wait)
     bool overlap_batches;                              // ELLC_OVERLAP=0 serialises consecutive batches (A/B measurement)
@@ -252,8 +253,11 @@ int ellc_create(const ellc_config* cfg, ellc_handle** out) {
     CR_TRY(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
     CR_TRY(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_greatest));
     for (int i = 0; i < 2; ++i) CR_TRY(cudaStreamCreateWithPriority(&h->tstream[i], cudaStreamNonBlocking, prio_greatest));
-    h->overlap_batches = true;
-    if (const char* e = std::getenv("ELLC_OVERLAP")) h->overlap_batches = (*e != '0');
+    // MEASURED (round 2, 4608 pairs per batch): letting batch k+1 start while batch k still runs does NOT just fill its last wave --
+    // its CTAs are dispatched as soon as its preparation is done, the two batches then share the SMs for most of their run time
+    // with two different working sets in L2: 270k tracks/s against 335k with the batches serialised.  Off unless ELLC_OVERLAP=1.
+    h->overlap_batches = false;
+    if (const char* e = std::getenv("ELLC_OVERLAP")) h->overlap_batches = (*e == '1');
     CR_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     CR_TRY(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
     CR_TRY(cudaStreamCreateWithPriority(&h->prep_stream, cudaStreamNonBlocking, prio_least));
@@ -945,12 +949,14 @@ int ellc_track_batch(ellc_handle* h, int32_t n, const ellc_pair* pairs, ellc_res
     return ELLC_OK;
 }
 
-int ellc_gn_evaluate(ellc_handle* h, int32_t kf_slot, int32_t frame_slot, int32_t level, const float pose[6],
-                     ellc_iter_trace* out, float* weight_image) {
+int ellc_gn_iterate(ellc_handle* h, int32_t kf_slot, int32_t frame_slot, int32_t level, int32_t variant, int32_t update,
+                    const float pose[6], ellc_iter_trace* out, float* weight_image, const ellc_display_planes* display) {
     if (!h) return ELLC_ERR_INVALID;
-    if (!pose || !out || level < 0 || level >= kLevels) { h->err = "bad evaluate arguments"; return ELLC_ERR_INVALID; }
+    if (!pose || !out || level < 0 || level >= kLevels || variant < 0 || variant > ELLC_VARIANT_PYRAMID) { h->err = "bad evaluate arguments"; return ELLC_ERR_INVALID; }
+    const bool lc = variant == ELLC_VARIANT_CONST_WEIGHT;
+    if (lc && (weight_image || display)) { h->err = "the constant-weight variant has no per-iteration weight / display images (src/PixelWisePyramid.cpp:687-913)"; return ELLC_ERR_INVALID; }
     ellc_pair pr;
-    pr.kf_slot = kf_slot; pr.frame_slot = frame_slot; pr.flags = 0;
+    pr.kf_slot = kf_slot; pr.frame_slot = frame_slot; pr.flags = lc ? ELLC_PAIR_CONST_WEIGHT : 0;
     for (int i = 0; i < 6; ++i) pr.init_pose[i] = pose[i];
     int rc = validate_pairs(h, 1, &pr);
     if (rc) return rc;
@@ -959,6 +965,7 @@ int ellc_gn_evaluate(ellc_handle* h, int32_t kf_slot, int32_t frame_slot, int32_
     if (rc) return rc;
     rc = main_waits_batches(h);
     if (rc) return rc;
+    if (lc) { rc = ensure_lc_pools(h); if (rc) return rc; }
     if (h->trace_cap < (int64_t)kLevels * ELLC_MAX_TRACE_ITERS) {
         cudaFree(h->d_trace); h->d_trace = nullptr; h->trace_cap = 0;
         CU_TRY(h, cudaMalloc(&h->d_trace, (size_t)kLevels * ELLC_MAX_TRACE_ITERS * sizeof(ellc_iter_trace)));
@@ -969,26 +976,64 @@ int ellc_gn_evaluate(ellc_handle* h, int32_t kf_slot, int32_t frame_slot, int32_
     rc = stage_h2d(h, d_pair, &pr, sizeof(pr));
     if (rc) return rc;
     const int64_t npx = (int64_t)h->geo.cols[level] * h->geo.rows[level];
-    if (weight_image) {
-        if (npx > h->weight_cap) {
-            cudaFree(h->d_weight); h->d_weight = nullptr; h->weight_cap = 0;
-            CU_TRY(h, cudaMalloc(&h->d_weight, (size_t)h->geo.win_off[1] * sizeof(float)));
-            h->weight_cap = h->geo.win_off[1];
-        }
-        CU_TRY(h, cudaMemsetAsync(h->d_weight, 0, (size_t)npx * sizeof(float), h->stream));
+    const bool want_disp = display && (display->warped_image || display->iteration_residual || display->warped_x || display->warped_y);
+    const int64_t need = npx * ((weight_image || want_disp) ? 1 : 0) + npx * (want_disp ? 4 : 0);
+    if (need > h->weight_cap) {
+        cudaFree(h->d_weight); h->d_weight = nullptr; h->weight_cap = 0;
+        CU_TRY(h, cudaMalloc(&h->d_weight, (size_t)h->geo.win_off[1] * 5 * sizeof(float)));
+        h->weight_cap = h->geo.win_off[1] * 5;
+    }
+    float* d_disp = h->d_weight ? h->d_weight + npx : nullptr;
+    if (weight_image || want_disp) CU_TRY(h, cudaMemsetAsync(h->d_weight, 0, (size_t)npx * sizeof(float), h->stream));
+    if (want_disp) {
+        // unselected pixels: display_warpedimg = display_iterationres = 0, savedWarpedPoints = -2 (src/PixelWisePyramid.cpp:207-221)
+        CU_TRY(h, cudaMemsetAsync(d_disp, 0, (size_t)npx * 2 * sizeof(float), h->stream));
+        h->launches += launch_fill_f32(h->stream, d_disp + 2 * npx, -2.0f, 2 * npx);
     }
     CU_TRY(h, cudaMemsetAsync(h->d_trace, 0, (size_t)kLevels * ELLC_MAX_TRACE_ITERS * sizeof(ellc_iter_trace), h->stream));
     TrackParams p;
     fill_params(h, p);
     p.pairs = d_pair; p.results = h->d_eval_result; p.trace = h->d_trace; p.n_pairs = 1;
-    p.level_hi = p.level_lo = level; p.iter_limit = 1; p.no_update = 1;
-    p.weight_out = weight_image ? h->d_weight : nullptr;
-    const int l = launch_track(h->stream, p, pick_cluster(h, 1), h->cfg.arithmetic == ELLC_ARITH_STRICT);
+    p.level_hi = p.level_lo = level; p.iter_limit = 1; p.no_update = update ? 0 : 1;
+    // flavour: the handle's, except that the matrix-form Pyramid.cpp variant and the display planes exist in STRICT only
+    bool strict = h->cfg.arithmetic == ELLC_ARITH_STRICT;
+    if (variant == ELLC_VARIANT_PYRAMID) { strict = true; p.jacobian_at_warped = 1; }
+    if (variant == ELLC_VARIANT_FORWARD && !h->cfg.jacobian_at_warped) p.jacobian_at_warped = 0;
+    if (want_disp) { strict = true; p.disp_out = d_disp; }
+    p.weight_out = (weight_image || want_disp) ? h->d_weight : nullptr;
+    const int l = lc ? launch_track_lc(h->stream, p, strict) : launch_track(h->stream, p, pick_cluster(h, 1), strict);
     if (l < 0) { h->err = std::string("track kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()); return ELLC_ERR_CUDA; }
     h->launches += l;
     CU_TRY(h, cudaMemcpyAsync(out, h->d_trace + (int64_t)level * ELLC_MAX_TRACE_ITERS, sizeof(ellc_iter_trace), cudaMemcpyDeviceToHost, h->stream));
     if (weight_image) CU_TRY(h, cudaMemcpyAsync(weight_image, h->d_weight, (size_t)npx * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (want_disp) {
+        float* dst[4] = {display->warped_image, display->iteration_residual, display->warped_x, display->warped_y};
+        for (int k = 0; k < 4; ++k)
+            if (dst[k]) CU_TRY(h, cudaMemcpyAsync(dst[k], d_disp + k * npx, (size_t)npx * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    }
     CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return ELLC_OK;
+}
+
+int ellc_gn_evaluate(ellc_handle* h, int32_t kf_slot, int32_t frame_slot, int32_t level, const float pose[6],
+                     ellc_iter_trace* out, float* weight_image) {
+    if (!h) return ELLC_ERR_INVALID;
+    return ellc_gn_iterate(h, kf_slot, frame_slot, level, h->cfg.jacobian_at_warped ? ELLC_VARIANT_PYRAMID : ELLC_VARIANT_FORWARD, 0,
+                           pose, out, weight_image, nullptr);
+}
+
+int ellc_hessian_inverse(ellc_handle* h, const float H[36], float Hinv[36], int32_t* regular) {
+    if (!h) return ELLC_ERR_INVALID;
+    if (!H || !Hinv) { h->err = "null argument"; return ELLC_ERR_INVALID; }
+    CU_TRY(h, cudaSetDevice(h->cfg.device));
+    float outv[37];
+    int rc = stage_h2d(h, h->d_small, H, 36 * sizeof(float));
+    if (rc) return rc;
+    h->launches += launch_invert6(h->stream, h->d_small, h->d_small + 64);
+    CU_TRY(h, cudaMemcpyAsync(outv, h->d_small + 64, sizeof(outv), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < 36; ++i) Hinv[i] = outv[i];
+    if (regular) *regular = outv[36] != 0.f ? 1 : 0;
     return ELLC_OK;
 }
 

@@ -116,6 +116,9 @@ struct TrackParams {
     float lm_lambda, lm_up, lm_down;   // Levenberg-Marquardt damping (0 = plain Gauss-Newton, the reference) and its step-rejection factors
     // multi-GPU result exchange (ellc_track_batch_exchange): besides `results`, the record of pair i is stored at
     // xchg_dst[d][xchg_index[i]] for d < xchg_n -- result tables in the memory of this or of peer GPUs (NVLink stores)
+    // display planes of the evaluated level (STRICT flavour, evaluate mode): 4 planes of cols x rows floats --
+    // display_warpedimg, display_iterationres, savedWarpedPointsX, savedWarpedPointsY (src/PixelWisePyramid.cpp:262-283, :332)
+    float* disp_out;
     int xchg_n;
     ellc_result* xchg_dst[ELLC_MAX_RANKS];
     const int* xchg_index;

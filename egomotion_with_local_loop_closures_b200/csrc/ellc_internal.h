@@ -32,6 +32,7 @@ int launch_lc_prepare(cudaStream_t st, const SelGeo* geo_pool, const SelPix* pix
                       const uint8_t* img_pool, int64_t img_slot_stride, const float* weight_pool, LcRec* lc_pool, float4* lcf_pool,
                       uint32_t* lcp_pool, float* lc_H, const LevelK* K, const int* d_slots, int n, const Geometry& geo);
 // dst (device, 4-byte aligned, capacity rounded up to 4 bytes) <- pinned host memory read by the SMs (no copy engine)
+int launch_fill_f32(cudaStream_t st, float* dst, float value, int64_t n);
 int launch_pull_host(cudaStream_t st, void* dst, const void* src_host_devptr, size_t bytes);
 
 // ellc_track.cu
@@ -46,6 +47,7 @@ int launch_xchg_store(cudaStream_t st, unsigned long long* d_counter, unsigned l
 // single-thread kernel running solve_update_f on the device (ellc_solve_update)
 // div2_rn_shared (the pixel loop's shared-reciprocal exact division) against __fdiv_rn on n pseudo-random operand triples
 int launch_div_selftest(cudaStream_t st, long long n, unsigned long long seed, unsigned long long* d_counts /*[2]*/);
+int launch_invert6(cudaStream_t st, const float* d_in /*H36*/, float* d_out /*Hinv36 ok1*/);
 int launch_solve_update(cudaStream_t st, const float* d_in /*H36 b6 pose6 weight6*/, float* d_out /*pose6 delta6 wp1 ok1 rt12 small1*/, int fast);
 
 }  // namespace ellc

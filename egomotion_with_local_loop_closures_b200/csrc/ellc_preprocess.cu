@@ -558,6 +558,15 @@ __global__ void pull_host_words_kernel(uint32_t* __restrict__ dst, const uint32_
 // ------------------------------------------------------------------------------------------------------------------
 // launch wrappers
 // ------------------------------------------------------------------------------------------------------------------
+__global__ void fill_f32_kernel(float* __restrict__ dst, float value, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = value;
+}
+int launch_fill_f32(cudaStream_t st, float* dst, float value, int64_t n) {
+    if (n <= 0) return 0;
+    fill_f32_kernel<<<148, 256, 0, st>>>(dst, value, n);
+    return 1;
+}
+
 int launch_pull_host(cudaStream_t st, void* dst, const void* src_host_devptr, size_t bytes) {
     const int n_words = (int)((bytes + 3) / 4);
     if (n_words <= 0) return 0;

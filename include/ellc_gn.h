@@ -272,7 +272,34 @@ int ellc_prepare_keyframes_lc(ellc_handle* h, int32_t n, const int32_t* kf_slots
 int ellc_gn_evaluate(ellc_handle* h, int32_t kf_slot, int32_t frame_slot, int32_t level, const float pose[6],
                      ellc_iter_trace* out, float* weight_image);
 
-/* hessian.inv() + updatePose() (src/PixelWisePyramid.cpp:451-491) executed by the device code path. */
+/* One iteration of any of the reference's three per-level drivers at a given pose, for callers that run the iteration loop
+ * themselves as src/ImageFunc.cpp:163-253 does:
+ *   ELLC_VARIANT_FORWARD       PixelWisePyramid::calculatePixelWiseParallel()                      (src/PixelWisePyramid.cpp:416-455)
+ *   ELLC_VARIANT_CONST_WEIGHT  PixelWisePyramid::calculatePixelWiseParallelInvCompositional(iter)   (:917-974; the precomputation of
+ *                              `iter == 0` -- steepest-descent rows, hessian, hessianInv -- is what ellc_prepare_keyframes_lc built)
+ *   ELLC_VARIANT_PYRAMID       Pyramid::performIterationSteps()                                      (src/Pyramid.cpp:714-726: Jacobian at
+ *                              the warped pixel; always the bit-faithful STRICT arithmetic)
+ * update = 0: normal equations only (out->delta / pose_after / weighted_pose stay 0); update = 1: hessian.inv() + updatePose() too.
+ * weight_image (display_weightimg) and the display planes (display_warpedimg, display_iterationres, savedWarpedPointsX / Y: 0 resp.
+ * -2 where the keyframe has no depth, -1 coordinates where the warp left the image, :207-283) are host arrays of (width >> level) x
+ * (height >> level) floats, any of them NULL; asking for display planes evaluates with the STRICT arithmetic. */
+#define ELLC_VARIANT_FORWARD      0
+#define ELLC_VARIANT_CONST_WEIGHT 1
+#define ELLC_VARIANT_PYRAMID      2
+typedef struct ellc_display_planes {
+    float* warped_image;              /* PixelWisePyramid::display_warpedimg                                        */
+    float* iteration_residual;        /* display_iterationres                                                       */
+    float* warped_x;                  /* savedWarpedPointsX                                                         */
+    float* warped_y;                  /* savedWarpedPointsY                                                         */
+} ellc_display_planes;
+int ellc_gn_iterate(ellc_handle* h, int32_t kf_slot, int32_t frame_slot, int32_t level, int32_t variant, int32_t update,
+                    const float pose[6], ellc_iter_trace* out, float* weight_image, const ellc_display_planes* display);
+/* hessianInv = hessian.inv() (src/PixelWisePyramid.cpp:451, :939; cv::Mat::inv, DECOMP_LU) by the device's LU; all zeros and
+ * *regular = 0 for a singular matrix, as OpenCV returns. */
+int ellc_hessian_inverse(ellc_handle* h, const float H[36], float Hinv[36], int32_t* regular);
+
+/* hessian.inv() + updatePose() (src/PixelWisePyramid.cpp:451-491) executed by the device code path of the handle's flavour
+ * (STRICT: Pade exponential / exact logarithm; FAST: closed-form exp / log below 11.5 degrees of rotation). */
 int ellc_solve_update(ellc_handle* h, const float H[36], const float b[6], const float pose_in[6],
                       float pose_out[6], float delta[6], float* weighted_pose);
 /* The same, also returning rows 0..2 of exp(hat(pose_out)) as K5 hands them to the next iteration (SE3_vec,
