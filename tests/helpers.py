@@ -60,11 +60,7 @@ def record(name, value, **extra):
 
 
 def iters_match(got, want, arith):
-    """Executed GN iterations per level.  STRICT runs the reference's Pade exponential / logarithm in K5: identical counts.  FAST
-    uses the closed-form small-angle exp / log there (allowed, +-1 iteration tolerated): a pose that differs
-    in the 7th digit can move weightedPose across the stop threshold one iteration earlier or later."""
-    got = [int(v) for v in got]
-    want = [int(v) for v in want]
-    if arith == 1:
-        return got == want
-    return all(abs(a - b) <= 1 for a, b in zip(got, want))
+    """Executed GN iterations per level: identical in both flavours.  (SURVEY.md section 7 would tolerate +-1 for the FAST flavour,
+    whose K5 uses the closed-form small-angle exp / log; measured on B200 the counts are identical on every test case, and the
+    kernel is run-to-run deterministic, so the tests assert equality.)"""
+    return [int(v) for v in got] == [int(v) for v in want]

@@ -86,9 +86,8 @@ def test_shim_tracks_like_the_reference_driver(tmp_path, oracle_mod):
         init = oracle_mod.concat_origin(prev_world, kf_world)                 # src/ImageFunc.cpp:106
         opose, otr = oracle_mod.track(ocfg, kf["image"], frames[i], kf["depth"], kf["var"], init)
         world = oracle_mod.concat_relative(opose, kf_world)                   # src/ImageFunc.cpp:306
-        # (the shim runs the FAST flavour: closed-form exp / log in K5, poses agree in the 6th digit)
-        assert np.abs(got_pose[i] - opose).max() < 1e-4 and np.abs(got_pose[i] - opose).max() < 1e-5
-        assert np.abs(got_world[i] - world).max() < 1e-5
+        assert np.abs(got_pose[i] - opose).max() < 1e-4 and np.abs(got_pose[i] - opose).max() < 2e-6
+        assert np.abs(got_world[i] - world).max() < 2e-6
         gt = synth.relative_pose(T[i + 1], np.eye(4))
         assert np.abs(got_pose[i] - gt).max() < 3e-3
         assert post[i][2:] == ["0", "0", str(otr["n_selected"][0]), str(w), str(h)]          # level-0 post-conditions
@@ -102,9 +101,9 @@ def test_shim_tracks_like_the_reference_driver(tmp_path, oracle_mod):
         Hinv, _ = oracle_mod.invert6(o["H"])
         pose, delta, wp = oracle_mod.update_pose(ocfg, Hinv, o["b"], pose)
         g = iters[it]
-        assert np.abs(np.array(g[2:8], np.float64) - pose).max() < 5e-6
-        assert abs(float(g[11]) - o["res_sum_f64"]) <= 1e-4 * o["res_sum_f64"]
-        assert abs(float(g[13]) - o["H_f64"][0, 0]) <= 1e-4 * o["H_f64"][0, 0]
+        assert np.abs(np.array(g[2:8], np.float64) - pose).max() < 2e-6
+        assert abs(float(g[11]) - o["res_sum_f64"]) <= 2.5e-5 * o["res_sum_f64"]
+        assert abs(float(g[13]) - o["H_f64"][0, 0]) <= 2.5e-5 * o["H_f64"][0, 0]
     assert [l for l in lines if l[0] == "count2"][0][1] == str(int((kf["depth"][2] > 0).sum()))
     # keyframe rebuilt from 1/depth hypotheses through depthMap::updateDepthImage (device pyramids)
     d0 = kf["depth"][0]
@@ -115,7 +114,7 @@ def test_shim_tracks_like_the_reference_driver(tmp_path, oracle_mod):
     assert abs(float(hyp[2]) - 100.0 * float((ref["valid_out"] != 0).sum()) / (w * h)) < 1e-3
     assert int(hyp[3]) == int((ref["depth"][1] > 0).sum()) and int(hyp[4]) == int((ref["depth"][3] > 0).sum())
     opose, _ = oracle_mod.track(ocfg, kf["image"], frames[0], ref["depth"], ref["var"], np.zeros(6, np.float32))
-    assert np.abs(np.array(hyp[5:8], np.float64) - opose[:3]).max() < 1e-5
+    assert np.abs(np.array(hyp[5:8], np.float64) - opose[:3]).max() < 2e-6
     # constant-weight loop-closure flow: weights saved by the sequential tracks, finalised, then one loop-closure pair
     h_, w_ = h, w
     wp = [np.zeros((h_ >> l, w_ >> l), np.float32) for l in range(4)]
@@ -159,7 +158,7 @@ def test_shim_against_the_reference_driver_fixture(tmp_path):
     pose = np.array([l for l in lines if l[0] == "pose"][0][2:8], np.float64)
     world = np.array([l for l in lines if l[0] == "world"][0][2:8], np.float64)
     post = [l for l in lines if l[0] == "post"][0]
-    assert np.abs(pose - g["p0_driver_pose"]).max() < 1e-5
-    assert np.abs(world - g["p0_driver_pose_wrt_world"]).max() < 1e-5
+    assert np.abs(pose - g["p0_driver_pose"]).max() < 2e-6
+    assert np.abs(world - g["p0_driver_pose_wrt_world"]).max() < 2e-6
     assert post[2:5] == ["0", "0", str(int(g["p0_n_selected"][0]))]          # both frames back at level 0, level-0 mask count
     assert [l for l in lines if l[0] == "pyr"][0][1:] == ["240", "135", "60", "34"]      # pyrDown dims at 480x270: (h+1)/2 rows
