@@ -75,7 +75,13 @@ SYMBOLS = ["ellc_default_config", "ellc_create", "ellc_destroy", "ellc_last_erro
            "ellc_prepare_keyframes_lc", "ellc_frame_histograms", "ellc_lc_gate", "ellc_upload_keyframe_hypotheses", "ellc_read_keyframe_occupancy", "ellc_read_keyframe_depth", "ellc_last_track_kernel_ms",
            "ellc_prepare_async", "ellc_batch_kernel_ms", "ellc_batch_interval_ms", "ellc_fence",
            "ellc_exchange_create", "ellc_exchange_attach_ipc", "ellc_exchange_attach_local", "ellc_track_batch_exchange",
-           "ellc_exchange_wait", "ellc_exchange_destroy", "ellc_se3_exp_closed", "ellc_se3_log_closed"]
+           "ellc_exchange_wait", "ellc_exchange_destroy", "ellc_se3_exp_closed", "ellc_se3_log_closed",
+           "ellc_gn_iterate", "ellc_hessian_inverse"]
+VARIANT_FORWARD, VARIANT_CONST_WEIGHT, VARIANT_PYRAMID = 0, 1, 2
+
+
+class DisplayPlanes(C.Structure):
+    _fields_ = [("warped_image", C.c_void_p), ("iteration_residual", C.c_void_p), ("warped_x", C.c_void_p), ("warped_y", C.c_void_p)]
 MAX_RANKS = 8
 IPC_HANDLE_BYTES = 64
 
@@ -150,6 +156,9 @@ def lib():
         L.ellc_exchange_wait.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
         L.ellc_exchange_destroy.argtypes = [C.c_void_p]
         L.ellc_se3_exp_closed.argtypes = [C.c_void_p] * 2
+        L.ellc_gn_iterate.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.POINTER(DisplayPlanes)]
+        L.ellc_hessian_inverse.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
         L.ellc_se3_log_closed.restype = C.c_int
         L.ellc_se3_log_closed.argtypes = [C.c_void_p] * 2
         _lib = L
@@ -325,6 +334,33 @@ class Tracker:
             w = np.zeros((rows, cols), np.float32)
         self._chk(lib().ellc_gn_evaluate(self._h, kf_slot, frame_slot, level, _p(pose), _p(out), _p(w)))
         return (out[0], w) if want_weights else out[0]
+
+    def gn_iterate(self, kf_slot, frame_slot, level, pose, variant=VARIANT_FORWARD, update=True, want_weights=False, want_display=False):
+        """One iteration of a reference per-level driver (ellc_gn_iterate).  Returns the trace record, plus the weight image and /
+        or a dict of the display planes when asked for."""
+        pose = np.ascontiguousarray(pose, np.float32)
+        out = np.zeros(1, TRACE_DTYPE)
+        cols, rows = self.level_dims(level)[2:]
+        w = np.zeros((rows, cols), np.float32) if want_weights else None
+        planes, dp = None, None
+        if want_display:
+            planes = {k: np.zeros((rows, cols), np.float32) for k in ("warped_image", "iteration_residual", "warped_x", "warped_y")}
+            dp = DisplayPlanes(*[planes[k].ctypes.data for k in ("warped_image", "iteration_residual", "warped_x", "warped_y")])
+        self._chk(lib().ellc_gn_iterate(self._h, kf_slot, frame_slot, level, int(variant), 1 if update else 0, _p(pose), _p(out), _p(w),
+                                        C.byref(dp) if dp is not None else None))
+        ret = [out[0]]
+        if want_weights:
+            ret.append(w)
+        if want_display:
+            ret.append(planes)
+        return ret[0] if len(ret) == 1 else tuple(ret)
+
+    def hessian_inverse(self, H):
+        H = np.ascontiguousarray(np.asarray(H, np.float32).reshape(36))
+        out = np.zeros(36, np.float32)
+        ok = C.c_int32()
+        self._chk(lib().ellc_hessian_inverse(self._h, _p(H), _p(out), C.byref(ok)))
+        return out.reshape(6, 6), bool(ok.value)
 
     def solve_update(self, H, b, pose):
         H = np.ascontiguousarray(np.asarray(H, np.float32).reshape(36))

@@ -28,7 +28,10 @@ extern bool FLAG_DO_PARALLEL_POSE_ESTIMATION;    // must stay true: this shim IS
 extern bool FLAG_INITIALIZE_NONZERO_POSE;
 extern bool FLAG_DO_CONST_WEIGHT_POSE_ESTIMATION;
 extern bool FLAG_DO_LOOP_CLOSURE;
+extern bool FLAG_ALTERNATE_GN_RA;                // batch alternation with rotation averaging ("LC" mode, src/main.cpp:89-92)
+extern bool FLAG_IS_BOOTSTRAP;
 extern int BATCH_START_ID;
+extern int BATCH_SIZE;
 
 #define UNZERO(val) (val < 0 ? (val > -1e-10 ? -1e-10 : val) : (val < 1e-10 ? 1e-10 : val))
 

@@ -2,8 +2,11 @@
 // one keyframe, consecutive frames, GetImagePoseEstimate initialised from the previous frame's world pose.
 // Input blob (written by tests/test_host_shim.py): int32 w, h, n_frames; f32 fx fy cx cy; u8 kf image; 4 depth levels;
 // 4 variance levels; n_frames u8 images.  Prints one line per result; the pytest side compares with the CPU oracle.
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <fstream>
 #include <sstream>
 #include <string>
@@ -15,6 +18,9 @@
 #include "ImageFunc.h"
 #include "PixelWisePyramid.h"
 #include "PoseFiles.h"
+#include "Pyramid.h"
+
+#include <thread>
 
 static void rd(FILE* f, void* p, size_t n) { if (fread(p, 1, n, f) != n) { fprintf(stderr, "short read\n"); exit(2); } }
 
@@ -43,7 +49,24 @@ int main(int argc, char** argv) {
         printf("posefiles ok %d %d %.9g\n", ok ? 1 : 0, fno, p[3]);
         return 0;
     }
-    if (argc > 2) { printf("link ok\n"); return 0; }
+    if (argc > 2 && std::string(argv[2]) == "--config") {
+        // host-only: main()'s argument handling and the batch parameters of config.txt (src/main.cpp:80-101, :132-137)
+        std::string msg;
+        const char* a1[] = {"ELLC"};
+        printf("cfg0 %d\n", ellc_host::configure_from_args(1, a1, &msg));
+        const char* a2[] = {"ELLC", "LC"};
+        int r = ellc_host::configure_from_args(2, a2, &msg);
+        printf("cfg1 %d %s\n", r, msg.c_str());
+        const char* a3[] = {"ELLC", "LC", "/nonexistent/config.txt"};
+        r = ellc_host::configure_from_args(3, a3, &msg);
+        printf("cfg2 %d %s\n", r, msg.c_str());
+        const char* a4[] = {"ELLC", "LC", argv[1]};
+        const int rc = ellc_host::configure_from_args(3, a4, &msg);
+        printf("cfg3 %d %d %d %d %d\n", rc, util::BATCH_START_ID, util::BATCH_SIZE, util::FLAG_IS_BOOTSTRAP ? 1 : 0, util::FLAG_ALTERNATE_GN_RA ? 1 : 0);
+        return 0;
+    }
+    const bool surface = argc > 2 && std::string(argv[2]) == "--surface";
+    if (argc > 2 && !surface) { printf("link ok\n"); return 0; }
     FILE* f = fopen(argv[1], "rb");
     if (!f) return 2;
     int w, h, n; float k[4];
@@ -59,6 +82,129 @@ int main(int argc, char** argv) {
         for (int l = 0; l < 4; ++l) rd(f, dm.depthvararrptr[l], (size_t)(w >> l) * (h >> l) * 4);
         dm.markDepthUpdated();
         printf("pyr %d %d %d %d\n", kf.image_pyramid[1].cols, kf.image_pyramid[1].rows, kf.image_pyramid[3].cols, kf.image_pyramid[3].rows);
+        if (surface) {
+            // ---- the rest of the reference's class surface ----------------------------------------------------
+            std::vector<frame*> fr;
+            for (int i = 0; i < n; ++i) { rd(f, img.data(), img.size()); fr.push_back(new frame(img.data(), w, h)); }
+            const int L = 1;
+            kf.updationOnPyrChange(L);
+            fr[0]->updationOnPyrChange(L, false);
+            // (a) frame::getInterpolatedElement, both overloads, inside / on the border / outside
+            const float pts[][2] = {{10.25f, 20.75f}, {0.0f, 0.0f}, {-0.5f, 3.2f}, {(float)(w >> L) - 1.0f, 5.5f}, {(float)(w >> L) - 0.5f, 5.5f},
+                                    {7.0f, (float)(h >> L) - 0.25f}, {-3.0f, -3.0f}, {33.999f, 41.001f}, {(float)(w >> L) + 2.0f, 1.0f}};
+            for (const auto& q : pts)
+                printf("interp %.9g %.9g %.9g %.9g %.9g %.9g\n", q[0], q[1], fr[0]->getInterpolatedElement(q[0], q[1], 1), fr[0]->getInterpolatedElement(q[0], q[1], 0),
+                       fr[0]->getInterpolatedElement(q[0], q[1], "gradx"), fr[0]->getInterpolatedElement(q[0], q[1], "grady"));
+            // (b) PixelWisePyramid with every display member, hessianInv, saveWeights(true / false)
+            float pose[6] = {0.002f, -0.001f, 0.0015f, 0.003f, -0.002f, 0.001f};
+            float pose_in[6];
+            for (int i = 0; i < 6; ++i) pose_in[i] = pose[i];
+            PixelWisePyramid pw(&kf, fr[0], pose, &dm);
+            pw.pose = pose;
+            pw.calculatePixelWiseParallel();
+            printf("pw_pose %.9g %.9g %.9g %.9g %.9g %.9g wp %.9g\n", pose[0], pose[1], pose[2], pose[3], pose[4], pose[5], pw.weightedPose);
+            double sw = 0, swarp = 0, sres = 0, sorig = 0; long n2 = 0, n1 = 0, tsum = 0, bsum = 0;
+            for (int y = 0; y < pw.nRows; ++y)
+                for (int x = 0; x < pw.nCols; ++x) {
+                    sw += pw.display_weightimg.ptr<float>(y)[x]; swarp += pw.display_warpedimg.ptr<float>(y)[x];
+                    sres += pw.display_iterationres.ptr<float>(y)[x]; sorig += pw.display_origres.ptr<float>(y)[x];
+                    n2 += pw.savedWarpedPointsX.ptr<float>(y)[x] == -2.0f; n1 += pw.savedWarpedPointsX.ptr<float>(y)[x] == -1.0f;
+                    tsum += pw.display_templateimg.ptr<unsigned char>(y)[x]; bsum += pw.display_2bewarpedimg.ptr<unsigned char>(y)[x];
+                }
+            printf("pw_disp %.9g %.9g %.9g %.9g %ld %ld %ld %ld\n", sw, swarp, sres, sorig, n2, n1, tsum, bsum);
+            // a few individual pixels of the planes (selected pixels in raster order) for an independent check on the Python side
+            int shown = 0;
+            for (int y = 0; y < pw.nRows && shown < 6; y += 7)
+                for (int x = 0; x < pw.nCols && shown < 6; x += 11)
+                    if (kf.mask.ptr<unsigned char>(y)[x]) {
+                        printf("pw_px %d %d %.9g %.9g %.9g %.9g %.9g\n", x, y, pw.savedWarpedPointsX.ptr<float>(y)[x], pw.savedWarpedPointsY.ptr<float>(y)[x],
+                               pw.display_warpedimg.ptr<float>(y)[x], pw.display_iterationres.ptr<float>(y)[x], pw.display_weightimg.ptr<float>(y)[x]);
+                        ++shown;
+                    }
+            double hh = 0;                                   // hessian * hessianInv ~ I
+            for (int i = 0; i < 6; ++i)
+                for (int j = 0; j < 6; ++j) {
+                    double s = 0;
+                    for (int k = 0; k < 6; ++k) s += (double)pw.hessian.ptr<float>(i)[k] * pw.hessianInv.ptr<float>(k)[j];
+                    hh = std::max(hh, std::fabs(s - (i == j ? 1.0 : 0.0)));
+                }
+            printf("pw_hinv %.3g\n", hh);
+            pw.saveWeights(true);
+            pw.saveWeights(true);
+            double ws = 0;
+            for (int i = 0; i < pw.nRows * pw.nCols; ++i) ws += kf.weight_pyramid[L].ptr<float>(0)[i];
+            printf("pw_save %d %.9g %.9g\n", kf.numWeightsAdded[L], ws, 2 * sw);
+            pw.saveWeights(false);
+            double cs = 0;
+            for (int i = 0; i < pw.nRows * pw.nCols; ++i) cs += fr[0]->weight_pyramid[L].ptr<float>(0)[i];
+            printf("pw_scatter %.9g\n", cs);
+            // (c) inverse-compositional constant-weight iterations through the class (weights = what saveWeights left, finalised)
+            kf.finaliseWeights();
+            float lpose[6] = {0, 0, 0, 0, 0, 0};
+            PixelWisePyramid pl(&kf, fr[1], lpose, &dm);
+            pl.pose = lpose;
+            for (int it = 0; it < 3; ++it) {
+                pl.calculatePixelWiseParallelInvCompositional(it);
+                printf("lc_iter %d %.9g %.9g %.9g %.9g %.9g %.9g wp %.9g H00 %.9g\n", it, lpose[0], lpose[1], lpose[2], lpose[3], lpose[4], lpose[5],
+                       pl.weightedPose, pl.hessian.ptr<float>(0)[0]);
+            }
+            // (d) class Pyramid (matrix form): performPrecomputation + two performIterationSteps
+            float ppose[6];
+            for (int i = 0; i < 6; ++i) ppose[i] = pose_in[i];
+            Pyramid py(&kf, fr[0], ppose, &dm);
+            py.performPrecomputation();
+            printf("pyr_pre %.9g %d\n", py.lastErr, py.weights.cols);
+            for (int it = 0; it < 2; ++it) {
+                const float ratio = py.performIterationSteps();
+                printf("pyr_iter %d %.9g %.9g %.9g %.9g %.9g %.9g %.9g ratio %.9g err %.9g\n", it, ppose[0], ppose[1], ppose[2], ppose[3], ppose[4], ppose[5],
+                       py.weightedPose, ratio, py.error);
+            }
+            // (e) calculateRandT post-condition of GetImagePoseEstimate (src/ImageFunc.cpp:307)
+            float init0[6] = {0, 0, 0, 0, 0, 0};
+            util::FLAG_DO_CONST_WEIGHT_POSE_ESTIMATION = false;
+            std::vector<float> p0 = GetImagePoseEstimate(&kf, fr[0], 2, &dm, &kf, init0);
+            printf("randt %.9g %.9g %.9g %.9g %.9g %.9g\n", fr[0]->SE3_R[1], fr[0]->SE3_R[5], fr[0]->SE3_T[0], fr[0]->SE3_T[2], fr[0]->SE3_Pose[15], fr[0]->Sim3_R[0]);
+            printf("world0 %.9g %.9g %.9g %.9g %.9g %.9g\n", fr[0]->poseWrtWorld[0], fr[0]->poseWrtWorld[1], fr[0]->poseWrtWorld[2], fr[0]->poseWrtWorld[3],
+                   fr[0]->poseWrtWorld[4], fr[0]->poseWrtWorld[5]);
+            // (f) two host threads, each with its own copies of the frames (the loop-closure thread, src/GlobalOptimize.cpp:181, :566-568):
+            //     both must reproduce the single-threaded poses bit for bit, concurrently, on separate contexts
+            std::vector<std::vector<float> > want;
+            for (int i = 0; i < n; ++i) { float z[6] = {0, 0, 0, 0, 0, 0}; want.push_back(GetImagePoseEstimate(&kf, fr[i], i + 2, &dm, &kf, z)); }
+            int bad[2] = {0, 0};
+            auto worker = [&](int t) {
+                try {
+                    frame kfc(kf);                                   // `new frame(*currentframe)`
+                    depthMap dmc;
+                    dmc.keyFrame = &kfc;
+                    for (int l = 0; l < 4; ++l) std::memcpy(dmc.depthvararrptr[l], dm.depthvararrptr[l], (size_t)(w >> l) * (h >> l) * 4);
+                    dmc.markDepthUpdated();
+                    for (int rep = 0; rep < 6; ++rep)
+                        for (int i = 0; i < n; ++i) {
+                            frame cur(*fr[i]);
+                            float z[6] = {0, 0, 0, 0, 0, 0};
+                            std::vector<float> p = GetImagePoseEstimate(&kfc, &cur, i + 2, &dmc, &kfc, z);
+                            for (int k = 0; k < 6; ++k) bad[t] += p[k] != want[i][k];
+                        }
+                } catch (const std::exception& e) { fprintf(stderr, "thread %d: %s\n", t, e.what()); bad[t] += 1000; }
+            };
+            std::thread t0(worker, 0), t1(worker, 1);
+            t0.join(); t1.join();
+            printf("threads %d %d contexts %d\n", bad[0], bad[1], ellc_host::context_count());
+            // (g) a batch with more distinct frames than there are frame slots (64): split into sub-batches, nothing overwritten
+            {
+                std::vector<frame*> copies, kfs; std::vector<depthMap*> dms; std::vector<float> inits;
+                for (int i = 0; i < 70; ++i) { copies.push_back(new frame(*fr[i % n])); kfs.push_back(&kf); dms.push_back(&dm); for (int k = 0; k < 6; ++k) inits.push_back(0.f); }
+                std::vector<float> out = ellc_host::TrackPairsBatched(kfs, dms, copies, inits);
+                int nb = 0;
+                for (int i = 0; i < 70; ++i) for (int k = 0; k < 6; ++k) nb += out[i * 6 + k] != want[i % n][k];
+                printf("bigbatch %d\n", nb);
+                for (frame* c : copies) delete c;
+            }
+            for (frame* c : fr) delete c;
+            ellc_host::shutdown();
+            fclose(f);
+            return 0;
+        }
         frame* prev = &kf;
         std::vector<frame*> frames;
         for (int i = 0; i < n; ++i) {
