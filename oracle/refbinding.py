@@ -10,29 +10,47 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "_ref", "libellc_ref.so")
 REFERENCE_SRC = "/root/reference/src"
 LEVELS = 4
 MAX_ITERS = 12
 
 
-def available():
+# Two builds of the same sources: the reference's compiled-in camera (480x270) and the metric resolution (640x480, generated
+# ExternVariable.h: see the Makefile).  select() switches the library every function of this module talks to.
+_VARIANTS = {"default": ("libellc_ref.so", "ref"), "640x480": ("libellc_ref_640x480.so", "ref640")}
+_variant = "default"
+
+
+def _so(variant=None):
+    return os.path.join(_HERE, "_ref", _VARIANTS[variant or _variant][0])
+
+
+def select(variant="default"):
+    """Use the build `variant` ("default" = 480x270 as shipped, "640x480") from now on; returns the previous selection."""
+    global _variant
+    assert variant in _VARIANTS
+    prev, _variant = _variant, variant
+    return prev
+
+
+def available(variant=None):
     """True if the library exists or can be built here (the reference sources are mounted)."""
-    return os.path.exists(_SO) or os.path.isdir(REFERENCE_SRC)
+    return os.path.exists(_so(variant)) or os.path.isdir(REFERENCE_SRC)
 
 
-def build(force=False):
+def build(force=False, variant=None):
+    so = _so(variant)
     if not os.path.isdir(REFERENCE_SRC):
-        if os.path.exists(_SO):
-            return _SO
-        raise RuntimeError("oracle/_ref/libellc_ref.so is missing and /root/reference is not mounted")
-    deps = [os.path.join(_HERE, "ref_driver.cpp")]
+        if os.path.exists(so):
+            return so
+        raise RuntimeError(so + " is missing and /root/reference is not mounted")
+    deps = [os.path.join(_HERE, "ref_driver.cpp"), os.path.join(_HERE, "Makefile")]
     for root, _, files in os.walk(os.path.join(_HERE, "shim")):
         deps += [os.path.join(root, f) for f in files]
-    stale = (not os.path.exists(_SO)) or any(os.path.getmtime(p) > os.path.getmtime(_SO) for p in deps)
+    stale = (not os.path.exists(so)) or any(os.path.getmtime(p) > os.path.getmtime(so) for p in deps)
     if force or stale:
-        subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
-    return _SO
+        subprocess.check_call(["make", "-C", _HERE, _VARIANTS[variant or _variant][1]], stdout=subprocess.DEVNULL)
+    return so
 
 
 class Iter(C.Structure):
@@ -45,14 +63,13 @@ class Trace(C.Structure):
                 ("final_pose", C.c_float * 6)]
 
 
-_lib = None
+_libs = {}
 
 
 def lib():
-    global _lib
-    if _lib is None:
-        _lib = C.CDLL(build())
-    return _lib
+    if _variant not in _libs:
+        _libs[_variant] = C.CDLL(build())
+    return _libs[_variant]
 
 
 def _p(a):

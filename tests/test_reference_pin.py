@@ -324,3 +324,91 @@ def test_reference_live_randomised_sweep(oracle_mod):
                     assert np.float32(o["weighted_pose"]) == q["weighted_pose"] and np.array_equal(o["pose_after"], q["pose_after"])
                     total += 1
     assert total > 100
+
+
+# ---- the reference's own code at the METRIC resolution (640x480) ----------------------------------------------------------
+live640 = pytest.mark.skipif(not ref.available("640x480"), reason="oracle/_ref/libellc_ref_640x480.so not built and /root/reference not mounted")
+
+
+@pytest.fixture(scope="module")
+def fx640():
+    return np.load(os.path.join(GOLD, "reference_track_640x480.npz"))
+
+
+def _pyramids640(g):
+    import sys
+    sys.path.insert(0, GOLD)
+    from make_reference_golden import digest
+    from make_reference_golden_640x480 import rebuild_pyramids
+    depth, var = rebuild_pyramids(g["depth0"])
+    assert [digest(a) for a in depth] == list(g["depth_sha"]) and [digest(a) for a in var] == list(g["var_sha"])
+    return depth, var
+
+
+def test_oracle_is_bit_identical_to_the_reference_at_640x480(oracle_mod, fx640):
+    """The committed fixture of the reference's own outputs at 640x480 (BASELINE.json's metric resolution; the reference's camera
+    is a compile-time constant, so this is a second build of the same unmodified sources -- tests/golden/
+    make_reference_golden_640x480.py): the oracle reproduces counts, iteration counts and every iteration's hessian / sd_param /
+    weightedPose / pose BIT FOR BIT, and the driver's result."""
+    g = fx640
+    depth, var = _pyramids640(g)
+    fxv, fyv, cx, cy = (float(v) for v in g["intr"])
+    ocfg = oracle_mod.default_config(640, 480, fx=fxv, fy=fyv, cx=cx, cy=cy)
+    n_it = 0
+    for i in range(len(g["frames"])):
+        pose, tr = oracle_mod.track(ocfg, g["kf_image"], g["frames"][i], depth, var, g["init"][i])
+        assert tr["n_selected"] == list(g[f"p{i}_n_selected"]) and tr["n_iters"] == list(g[f"p{i}_n_iters"]), i
+        assert np.array_equal(pose, g[f"p{i}_pose"]), i
+        for l in range(4):
+            for k, o in enumerate(tr["levels"][l]):
+                assert np.array_equal(np.asarray(o["H"], np.float32).reshape(6, 6), g[f"p{i}_H_{l}"][k]), (i, l, k)
+                assert np.array_equal(o["b"], g[f"p{i}_b_{l}"][k]) and np.float32(o["weighted_pose"]) == g[f"p{i}_wp_{l}"][k], (i, l, k)
+                assert np.array_equal(o["pose_after"], g[f"p{i}_pose_{l}"][k]), (i, l, k)
+                n_it += 1
+        # GetImagePoseEstimate with the t-1 frame at world pose init and the keyframe at the origin (src/ImageFunc.cpp:97-108, :305-306)
+        init = oracle_mod.concat_origin(g["init"][i], np.zeros(6, np.float32))
+        dpose, _ = oracle_mod.track(ocfg, g["kf_image"], g["frames"][i], depth, var, init)
+        assert np.array_equal(dpose, g[f"p{i}_driver_pose"]), i
+        assert np.array_equal(oracle_mod.concat_relative(dpose, np.zeros(6, np.float32)), g[f"p{i}_driver_pose_wrt_world"]), i
+    assert n_it > 20
+
+
+@live640
+def test_fixture_640x480_is_what_the_reference_produces(fx640):
+    prev = ref.select("640x480")
+    try:
+        k = ref.dims()
+        assert (k["width"], k["height"], float(k["fx"]), float(k["cx"]), float(k["cy"])) == (640, 480, 512.0, 320.0, 240.0)
+        g = fx640
+        depth, var = _pyramids640(g)
+        tr = ref.track_trace(g["kf_image"], g["frames"][1], depth, var, g["init"][1])
+        assert tr["n_iters"] == list(g["p1_n_iters"]) and np.array_equal(tr["final_pose"], g["p1_pose"])
+    finally:
+        ref.select(prev)
+
+
+@live640
+def test_reference_live_random_pairs_at_640x480(oracle_mod, scene_vga):
+    """Fresh pairs at 640x480 (the parity tests' own scene_vga case and two perturbed starts): oracle vs the reference's own code,
+    bit-identical at every iteration."""
+    prev = ref.select("640x480")
+    try:
+        case = scene_vga
+        ocfg = oracle_mod.default_config(640, 480, fx=512.0, fy=512.0, cx=320.0, cy=240.0)
+        kf = case["kf"]
+        runs = [(case["frames"][0], np.zeros(6, np.float32)), (case["frames"][1], (case["gt"][1] * 0.5).astype(np.float32)),
+                (case["frames"][0], (case["gt"][0] * 1.4).astype(np.float32))]
+        total = 0
+        for n, (fr, init) in enumerate(runs):
+            pose, tr = oracle_mod.track(ocfg, kf["image"], fr, kf["depth"], kf["var"], init)
+            r = ref.track_trace(kf["image"], fr, kf["depth"], kf["var"], init)
+            assert tr["n_selected"] == r["n_selected"] and tr["n_iters"] == r["n_iters"], n
+            assert np.array_equal(pose, r["final_pose"]), n
+            for l in range(4):
+                for o, q in zip(tr["levels"][l], r["levels"][l]):
+                    assert np.array_equal(np.asarray(o["H"], np.float32).reshape(6, 6), q["H"]) and np.array_equal(o["b"], q["b"]), (n, l)
+                    assert np.float32(o["weighted_pose"]) == q["weighted_pose"] and np.array_equal(o["pose_after"], q["pose_after"]), (n, l)
+                    total += 1
+        assert total > 30
+    finally:
+        ref.select(prev)
