@@ -60,7 +60,10 @@ TRACE_DTYPE = np.dtype([("H", "<f4", 36), ("b", "<f4", 6), ("delta", "<f4", 6), 
                         ("executed", "<i4"), ("lm_lambda", "<f4"), ("lm_rejected", "<i4"), ("pad", "<i4", 3)])
 LC_CAND_DTYPE = np.dtype([("loop_frame_slot", "<i4"), ("test_frame_slot", "<i4"), ("loop_pose_world", "<f4", 6), ("test_pose_world", "<f4", 6)])
 LC_STATS_DTYPE = np.dtype([("match_value", "<f8"), ("rms_error", "<f4"), ("relative_view_angle", "<f4"), ("pass", "<i4"), ("reserved", "<i4")])
-assert LC_CAND_DTYPE.itemsize == 56 and LC_STATS_DTYPE.itemsize == 24
+LC_RING_DTYPE = np.dtype([("frame_id", "<i4"), ("is_valid", "<i4"), ("frame_slot", "<i4"), ("kf_slot", "<i4"), ("pose_world", "<f4", 6)])
+LC_QUERY_DTYPE = np.dtype([("current_array_id", "<i4"), ("match_window_beg", "<i4"), ("match_window_end", "<i4"), ("frame_id", "<i4"),
+                           ("frame_slot", "<i4"), ("stray", "<i4"), ("pose_world", "<f4", 6)])
+assert LC_CAND_DTYPE.itemsize == 56 and LC_STATS_DTYPE.itemsize == 24 and LC_RING_DTYPE.itemsize == 40 and LC_QUERY_DTYPE.itemsize == 48
 assert PAIR_DTYPE.itemsize == 36 and RESULT_DTYPE.itemsize == 256 and TRACE_DTYPE.itemsize == 256
 
 # every symbol include/ellc_gn.h declares
@@ -76,7 +79,7 @@ SYMBOLS = ["ellc_default_config", "ellc_create", "ellc_destroy", "ellc_last_erro
            "ellc_prepare_async", "ellc_batch_kernel_ms", "ellc_batch_interval_ms", "ellc_fence",
            "ellc_exchange_create", "ellc_exchange_attach_ipc", "ellc_exchange_attach_local", "ellc_track_batch_exchange",
            "ellc_exchange_wait", "ellc_exchange_destroy", "ellc_se3_exp_closed", "ellc_se3_log_closed",
-           "ellc_gn_iterate", "ellc_hessian_inverse"]
+           "ellc_gn_iterate", "ellc_hessian_inverse", "ellc_lc_generate_pairs", "ellc_track_generated_pairs"]
 VARIANT_FORWARD, VARIANT_CONST_WEIGHT, VARIANT_PYRAMID = 0, 1, 2
 
 
@@ -159,6 +162,9 @@ def lib():
         L.ellc_gn_iterate.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.POINTER(DisplayPlanes)]
         L.ellc_hessian_inverse.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
+        L.ellc_lc_generate_pairs.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_int32,
+                                             C.POINTER(C.c_int32), C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ellc_track_generated_pairs.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.ellc_se3_log_closed.restype = C.c_int
         L.ellc_se3_log_closed.argtypes = [C.c_void_p] * 2
         _lib = L
@@ -444,6 +450,22 @@ class Tracker:
         out = np.zeros(n, LC_STATS_DTYPE)
         self._chk(lib().ellc_lc_gate(self._h, n, _p(cand), float(match_threshold), float(max_rel_view_angle), _p(out)))
         return out
+
+    def lc_generate_pairs(self, ring, queries, min_match_difference=8, match_threshold=0.1, max_rel_view_angle=10.0, pair_flags=0):
+        """findMatch's ring walk + gating for all queries on the device.  Returns (pairs, stats, query_of_pair); the list also
+        stays on the device for track_generated_pairs()."""
+        ring = np.ascontiguousarray(ring, LC_RING_DTYPE); queries = np.ascontiguousarray(queries, LC_QUERY_DTYPE)
+        cap = max(1, len(ring) * len(queries))
+        pairs = np.zeros(cap, PAIR_DTYPE); stats = np.zeros(cap, LC_STATS_DTYPE); qi = np.zeros(cap, np.int32)
+        n = C.c_int32()
+        self._chk(lib().ellc_lc_generate_pairs(self._h, len(ring), _p(ring), len(queries), _p(queries), int(min_match_difference),
+                                               float(match_threshold), float(max_rel_view_angle), int(pair_flags), C.byref(n), _p(pairs), _p(stats), _p(qi)))
+        return pairs[:n.value], stats[:n.value], qi[:n.value]
+
+    def track_generated_pairs(self, n_pairs):
+        res = np.zeros(n_pairs, RESULT_DTYPE)
+        self._chk(lib().ellc_track_generated_pairs(self._h, int(n_pairs), _p(res)))
+        return res
 
     # -- constant-weight loop-closure variant
     def reset_keyframe_weights(self, kf_slot):

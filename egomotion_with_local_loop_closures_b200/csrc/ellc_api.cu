@@ -100,6 +100,11 @@ struct ellc_handle {
     ellc_pair* d_pairs; ellc_result* d_results; int* d_order;       // entry of the batch being launched / launched last
     ellc_result* d_eval_result;                        // ellc_gn_evaluate's own record (never clobbers an undownloaded batch)
     ellc_exchange* xc;                                 // multi-GPU result exchange (ellc_exchange_create), or null
+    // device-side loop-closure pair list (ellc_lc_generate_pairs): one allocation carved into ring / queries / per-query segments /
+    // packed list / statistics / query index / total
+    char* d_gen; size_t gen_bytes; int gen_cap_q, gen_cap_ring;
+    ellc_pair* d_gen_pairs; int gen_n, gen_flags;
+    std::vector<int> gen_kf_slots, gen_frame_slots;    // slots the generated pairs may read (slot-reuse bookkeeping)
     ellc_iter_trace* d_trace; int64_t trace_cap;
     float* d_small;                                    // 128 floats in/out for solve_update
     float* d_weight; int64_t weight_cap;
@@ -188,7 +193,7 @@ int ellc_destroy(ellc_handle* h) {
     cudaFree(h->kf_mask); cudaFree(h->kf_geo); cudaFree(h->kf_pix); cudaFree(h->kf_ikf);
     cudaFree(h->d_hyp); cudaFree(h->d_nvalid); cudaFree(h->fr_hist);
     cudaFree(h->fr_weight); cudaFree(h->kf_weight); cudaFree(h->kf_lc); cudaFree(h->kf_lcH); cudaFree(h->kf_lcf); cudaFree(h->kf_lcp); cudaFree(h->kf_count); cudaFree(h->kf_rowcount); cudaFree(h->kf_rowoff);
-    cudaFree(h->d_slots); cudaFree(h->d_slots_p); cudaFree(h->d_trace); cudaFree(h->d_small); cudaFree(h->d_eval_result);
+    cudaFree(h->d_slots); cudaFree(h->d_slots_p); cudaFree(h->d_trace); cudaFree(h->d_small); cudaFree(h->d_eval_result); cudaFree(h->d_gen);
     for (int r = 0; r < 4; ++r) { cudaFree(h->d_pairs4[r]); cudaFree(h->d_results4[r]); cudaFree(h->d_order4[r]); cudaFree(h->d_gidx4[r]); }
     cudaFree(h->d_weight);
     if (h->h_pin) cudaFreeHost(h->h_pin);
@@ -557,8 +562,17 @@ struct XchgLaunch {
     const int32_t* global_index = nullptr;                 // host
 };
 
-static int track_launch(ellc_handle* h, int n, const ellc_pair* pairs, bool want_trace, const XchgLaunch* xl = nullptr) {
-    int rc = validate_pairs(h, n, pairs);
+// A pair list that already lives on the device (ellc_lc_generate_pairs): no staging, no host-side schedule
+struct DevicePairs {
+    const ellc_pair* d_pairs;
+    int flags;                                             // the same ELLC_PAIR_* flags on every pair
+    const std::vector<int>* kf_slots;
+    const std::vector<int>* frame_slots;
+};
+
+static int track_launch(ellc_handle* h, int n, const ellc_pair* pairs, bool want_trace, const XchgLaunch* xl = nullptr,
+                        const DevicePairs* dev = nullptr) {
+    int rc = dev ? ELLC_OK : validate_pairs(h, n, pairs);
     if (rc) return rc;
     CU_TRY(h, cudaSetDevice(h->cfg.device));
     rc = flush_dirty(h);
@@ -581,8 +595,11 @@ static int track_launch(ellc_handle* h, int n, const ellc_pair* pairs, bool want
     // Constant-weight (loop-closure) pairs run in their own kernel: the schedule lists the forward pairs first.
     int n_fwd = 0;
     bool save_weights = false;
-    std::vector<int> order(n);
-    {
+    std::vector<int> order(dev ? 0 : n);
+    if (dev) {                                             // generated lists are query-major = frame-major already
+        n_fwd = (dev->flags & ELLC_PAIR_CONST_WEIGHT) ? 0 : n;
+        save_weights = (dev->flags & ELLC_PAIR_SAVE_WEIGHTS) != 0;
+    } else {
         for (int i = 0; i < n; ++i) order[i] = i;
         int kf_group = 0;                                  // EXPERIMENT: keyframes per schedule group (0 = frame-major over all keyframes)
         if (const char* e = std::getenv("ELLC_ORDER_KF_GROUP")) kf_group = std::atoi(e);
@@ -612,10 +629,12 @@ static int track_launch(ellc_handle* h, int n, const ellc_pair* pairs, bool want
     CU_TRY(h, cudaStreamWaitEvent(ts, h->main_ev, 0));
     const bool serial = !h->overlap_batches || want_trace || save_weights || n_fwd < n;
     if (serial && seq > 1 && seq - 1 > h->batch_done_seq) CU_TRY(h, cudaStreamWaitEvent(ts, h->batch_ev[(seq - 1) & 3], 0));
-    rc = stage_h2d_on(h, ts, h->d_pairs, pairs, (size_t)n * sizeof(ellc_pair));
-    if (rc) return rc;
-    rc = stage_h2d_on(h, ts, h->d_order, order.data(), (size_t)n * sizeof(int));
-    if (rc) return rc;
+    if (!dev) {
+        rc = stage_h2d_on(h, ts, h->d_pairs, pairs, (size_t)n * sizeof(ellc_pair));
+        if (rc) return rc;
+        rc = stage_h2d_on(h, ts, h->d_order, order.data(), (size_t)n * sizeof(int));
+        if (rc) return rc;
+    }
     if (xl && xl->n_dst > 0) {
         rc = stage_h2d_on(h, ts, h->d_gidx4[r], xl->global_index, (size_t)n * sizeof(int));
         if (rc) return rc;
@@ -623,7 +642,8 @@ static int track_launch(ellc_handle* h, int n, const ellc_pair* pairs, bool want
     if (want_trace) CU_TRY(h, cudaMemsetAsync(h->d_trace, 0, (size_t)n * kLevels * ELLC_MAX_TRACE_ITERS * sizeof(ellc_iter_trace), ts));
     TrackParams p;
     fill_params(h, p);
-    p.pairs = h->d_pairs; p.order = h->d_order; p.results = h->d_results; p.trace = want_trace ? h->d_trace : nullptr; p.n_pairs = n;
+    p.pairs = dev ? dev->d_pairs : h->d_pairs; p.order = dev ? nullptr : h->d_order; p.results = h->d_results;
+    p.trace = want_trace ? h->d_trace : nullptr; p.n_pairs = n;
     if (xl && xl->n_dst > 0) {
         p.xchg_n = xl->n_dst;
         for (int d = 0; d < xl->n_dst; ++d) p.xchg_dst[d] = xl->dst[d];
@@ -642,7 +662,7 @@ static int track_launch(ellc_handle* h, int n, const ellc_pair* pairs, bool want
     if (l < 0) { h->err = std::string("track kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()); return ELLC_ERR_CUDA; }
     h->launches += l;
     if (n_fwd < n) {
-        p.order = h->d_order + n_fwd;
+        p.order = dev ? nullptr : h->d_order + n_fwd;
         p.n_pairs = n - n_fwd;
         l = launch_track_lc(ts, p, h->cfg.arithmetic == ELLC_ARITH_STRICT);
         if (l < 0) { h->err = std::string("loop-closure track kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()); return ELLC_ERR_CUDA; }
@@ -652,7 +672,12 @@ static int track_launch(ellc_handle* h, int n, const ellc_pair* pairs, bool want
     CU_TRY(h, cudaEventRecord(h->batch_ev[r], ts));
     h->batch_seq = seq;
     h->res_seq[r] = seq;
-    for (int i = 0; i < n; ++i) { h->fr_reader[pairs[i].frame_slot] = seq; h->kf_reader[pairs[i].kf_slot] = seq; }
+    if (dev) {
+        for (int v : *dev->frame_slots) h->fr_reader[v] = seq;
+        for (int v : *dev->kf_slots) h->kf_reader[v] = seq;
+    } else {
+        for (int i = 0; i < n; ++i) { h->fr_reader[pairs[i].frame_slot] = seq; h->kf_reader[pairs[i].kf_slot] = seq; }
+    }
     CU_TRY(h, cudaGetLastError());
     return ELLC_OK;
 }
@@ -820,6 +845,91 @@ int ellc_lc_gate(ellc_handle* h, int32_t n, const ellc_lc_candidate* cand, float
     CU_TRY(h, cudaMemcpyAsync(stats, d_out, out_bytes, cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(h, cudaFreeAsync(d_buf, h->stream));
     CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return ELLC_OK;
+}
+
+int ellc_lc_generate_pairs(ellc_handle* h, int32_t ring_len, const ellc_lc_ring_entry* ring, int32_t n_queries, const ellc_lc_query* queries,
+                           int32_t min_match_difference, float match_threshold, float max_rel_view_angle, int32_t pair_flags,
+                           int32_t* n_pairs, ellc_pair* pairs, ellc_lc_stats* stats, int32_t* query_of_pair) {
+    if (!h) return ELLC_ERR_INVALID;
+    if (ring_len < 1 || ring_len > 64 || n_queries < 0 || !ring || (n_queries > 0 && !queries) || !n_pairs) { h->err = "bad ring / query arguments (ring_len <= 64)"; return ELLC_ERR_INVALID; }
+    if ((pair_flags & ELLC_PAIR_CONST_WEIGHT) && (pair_flags & ELLC_PAIR_SAVE_WEIGHTS)) { h->err = "a pair cannot both use constant weights and save weights"; return ELLC_ERR_INVALID; }
+    *n_pairs = 0;
+    h->gen_n = 0;
+    h->gen_kf_slots.clear(); h->gen_frame_slots.clear();
+    if (n_queries == 0) return ELLC_OK;
+    for (int i = 0; i < ring_len; ++i) {
+        if (!ring[i].is_valid) continue;
+        const int fs = ring[i].frame_slot, ks = ring[i].kf_slot;
+        if (fs < 0 || fs >= h->cfg.max_frames || ks < 0 || ks >= h->cfg.max_keyframes) { h->err = "ring entry references a slot out of range"; return ELLC_ERR_INVALID; }
+        if (!h->fr_hist || !h->fr_hist_ready[fs]) { h->err = "ring entry without histogram: call ellc_frame_histograms first"; return ELLC_ERR_NOT_READY; }
+        if (h->kf_state[ks] == 0) { h->err = "ring entry references a keyframe slot that was never uploaded"; return ELLC_ERR_NOT_READY; }
+        if ((pair_flags & ELLC_PAIR_CONST_WEIGHT) && !h->kf_lc_ready[ks]) { h->err = "constant-weight pairs on a keyframe without loop-closure records"; return ELLC_ERR_NOT_READY; }
+        h->gen_kf_slots.push_back(ks);
+    }
+    for (int q = 0; q < n_queries; ++q) {
+        const int fs = queries[q].frame_slot;
+        if (fs < 0 || fs >= h->cfg.max_frames || queries[q].current_array_id < 0 || queries[q].current_array_id > ring_len ||
+            queries[q].match_window_beg < 0 || queries[q].match_window_beg >= ring_len || queries[q].match_window_end < 0 ||
+            queries[q].match_window_end >= ring_len) { h->err = "query references a slot / ring position out of range"; return ELLC_ERR_INVALID; }
+        if (h->fr_state[fs] == 0 || !h->fr_hist || !h->fr_hist_ready[fs]) { h->err = "query frame without histogram: call ellc_frame_histograms first"; return ELLC_ERR_NOT_READY; }
+        h->gen_frame_slots.push_back(fs);
+    }
+    CU_TRY(h, cudaSetDevice(h->cfg.device));
+    int rc = main_waits_batches(h);
+    if (rc) return rc;
+    const size_t cap = (size_t)n_queries * ring_len;
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t o_ring = 0, o_q = o_ring + up((size_t)ring_len * sizeof(ellc_lc_ring_entry)), o_segp = o_q + up((size_t)n_queries * sizeof(ellc_lc_query)),
+                 o_segs = o_segp + up(cap * sizeof(ellc_pair)), o_segc = o_segs + up(cap * sizeof(ellc_lc_stats)), o_p = o_segc + up((size_t)n_queries * sizeof(int)),
+                 o_s = o_p + up(cap * sizeof(ellc_pair)), o_qi = o_s + up(cap * sizeof(ellc_lc_stats)), o_t = o_qi + up(cap * sizeof(int)), total = o_t + 256;
+    if (total > h->gen_bytes) {
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+        for (int i = 0; i < 2; ++i) CU_TRY(h, cudaStreamSynchronize(h->tstream[i]));      // a batch may still read the previous list
+        cudaFree(h->d_gen); h->d_gen = nullptr; h->gen_bytes = 0;
+        CU_TRY(h, cudaMalloc(&h->d_gen, total));
+        h->gen_bytes = total;
+    }
+    char* g = h->d_gen;
+    rc = stage_h2d(h, g + o_ring, ring, (size_t)ring_len * sizeof(ellc_lc_ring_entry));
+    if (rc) return rc;
+    rc = stage_h2d(h, g + o_q, queries, (size_t)n_queries * sizeof(ellc_lc_query));
+    if (rc) return rc;
+    const int l = launch_lc_generate(h->stream, h->fr_hist, reinterpret_cast<ellc_lc_ring_entry*>(g + o_ring), ring_len, reinterpret_cast<ellc_lc_query*>(g + o_q),
+                                     n_queries, min_match_difference, match_threshold, max_rel_view_angle, pair_flags, reinterpret_cast<ellc_pair*>(g + o_segp),
+                                     reinterpret_cast<ellc_lc_stats*>(g + o_segs), reinterpret_cast<int*>(g + o_segc), reinterpret_cast<ellc_pair*>(g + o_p),
+                                     reinterpret_cast<ellc_lc_stats*>(g + o_s), reinterpret_cast<int*>(g + o_qi), reinterpret_cast<int*>(g + o_t));
+    if (l < 0) { h->err = "pair-list kernels: bad launch configuration"; return ELLC_ERR_INVALID; }
+    h->launches += l;
+    CU_TRY(h, cudaGetLastError());
+    int n = 0;
+    CU_TRY(h, cudaMemcpyAsync(&n, g + o_t, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    if (n > 0) {
+        if (pairs) CU_TRY(h, cudaMemcpyAsync(pairs, g + o_p, (size_t)n * sizeof(ellc_pair), cudaMemcpyDeviceToHost, h->stream));
+        if (stats) CU_TRY(h, cudaMemcpyAsync(stats, g + o_s, (size_t)n * sizeof(ellc_lc_stats), cudaMemcpyDeviceToHost, h->stream));
+        if (query_of_pair) CU_TRY(h, cudaMemcpyAsync(query_of_pair, g + o_qi, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+    }
+    h->d_gen_pairs = reinterpret_cast<ellc_pair*>(g + o_p);
+    h->gen_n = n; h->gen_flags = pair_flags;
+    *n_pairs = n;
+    return ELLC_OK;
+}
+
+int ellc_track_generated_pairs(ellc_handle* h, int32_t n_pairs, ellc_result* results) {
+    if (!h) return ELLC_ERR_INVALID;
+    if (n_pairs < 0 || n_pairs != h->gen_n || (n_pairs > 0 && !results)) { h->err = "n_pairs is not what the last ellc_lc_generate_pairs reported / null results"; return ELLC_ERR_INVALID; }
+    if (n_pairs == 0) return ELLC_OK;
+    for (int ks : h->gen_kf_slots)
+        if ((h->gen_flags & ELLC_PAIR_CONST_WEIGHT) && !h->kf_lc_ready[ks]) { h->err = "a keyframe of the generated list lost its loop-closure records"; return ELLC_ERR_NOT_READY; }
+    DevicePairs dev = {h->d_gen_pairs, h->gen_flags, &h->gen_kf_slots, &h->gen_frame_slots};
+    int rc = track_launch(h, n_pairs, nullptr, false, nullptr, &dev);
+    if (rc) return rc;
+    cudaStream_t ts = h->tstream[h->batch_seq & 1];
+    CU_TRY(h, cudaMemcpyAsync(results, h->d_results, (size_t)n_pairs * sizeof(ellc_result), cudaMemcpyDeviceToHost, ts));
+    CU_TRY(h, cudaStreamSynchronize(ts));
+    note_done(h, h->batch_seq);
     return ELLC_OK;
 }
 

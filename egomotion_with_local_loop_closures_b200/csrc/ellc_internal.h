@@ -18,6 +18,11 @@ int launch_select(cudaStream_t st, const float* depth_pool, const float* var_poo
 // per-candidate statistics (ellc_track.cu, next to the pose algebra)
 int launch_frame_histograms(cudaStream_t st, const uint8_t* img_pool, int64_t img_slot_stride, const int* d_slots, int n, int n_pixels,
                             float* hist_pool);
+// the ring walk of findMatch on the device: compacted, query-major list of passing (loop frame, test frame) pairs as ellc_pair records
+int launch_lc_generate(cudaStream_t st, const float* hist_pool, const ellc_lc_ring_entry* d_ring, int ring_len, const ellc_lc_query* d_queries,
+                       int n_queries, int min_match_difference, float match_threshold, float max_rel_view_angle, int pair_flags,
+                       ellc_pair* d_seg_pairs, ellc_lc_stats* d_seg_stats, int* d_seg_count, ellc_pair* d_pairs, ellc_lc_stats* d_stats,
+                       int* d_query_of_pair, int* d_total);
 int launch_lc_gate(cudaStream_t st, const float* hist_pool, const ellc_lc_candidate* d_cand, int n, float match_threshold,
                    float max_rel_view_angle, ellc_lc_stats* d_out);
 // keyframe depth / variance pyramids from hypotheses (src/DepthPropagation.cpp:1254-1306, :1637-1719); depth_slot / var_slot are

@@ -136,6 +136,25 @@ typedef struct ellc_lc_stats {
     int32_t reserved;
 } ellc_lc_stats;
 
+/* Loop-closure pair-list generation on the device (globalOptimize::findMatchParallel + findMatch, src/GlobalOptimize.cpp:274-420,
+ * :455-620): one entry of loopFrameArray, and one test frame whose matches are wanted. */
+typedef struct ellc_lc_ring_entry {
+    int32_t frame_id;                 /* loopFrameArray[i].frameId                                                    */
+    int32_t is_valid;                 /* loopFrameArray[i].isValid                                                    */
+    int32_t frame_slot;               /* frame slot holding its image (histogram computed by ellc_frame_histograms)   */
+    int32_t kf_slot;                  /* keyframe slot holding this_frame + this_currentDepthMap: the pair's keyframe */
+    float   pose_world[6];            /* loopFrameArray[i].poseWrtWorld                                               */
+} ellc_lc_ring_entry;                 /* 40 B */
+typedef struct ellc_lc_query {
+    int32_t current_array_id;         /* currentArrayId: the walk starts one position below, :286                     */
+    int32_t match_window_beg;         /* match_window_beg / match_window_end, :312-322                                */
+    int32_t match_window_end;
+    int32_t frame_id;                 /* testFrame->frameId (MIN_MATCH_DIFFERENCE test, :344)                         */
+    int32_t frame_slot;               /* frame slot of the test frame (histogram computed)                            */
+    int32_t stray;                    /* strayFlag: no pose, only the id gap gates, :356-378                          */
+    float   pose_world[6];            /* currentLoopFrame.poseWrtWorld                                                */
+} ellc_lc_query;                      /* 48 B */
+
 typedef struct ellc_handle ellc_handle;
 
 /* ---- lifetime -------------------------------------------------------------------------------------------------- */
@@ -183,6 +202,22 @@ int ellc_read_keyframe_depth(ellc_handle* h, int32_t slot, int32_t level, float*
 int ellc_frame_histograms(ellc_handle* h, int32_t n, const int32_t* frame_slots, float* hist);
 int ellc_lc_gate(ellc_handle* h, int32_t n, const ellc_lc_candidate* candidates, float match_threshold, float max_rel_view_angle,
                  ellc_lc_stats* stats);
+
+/* The ring / window walk of findMatch for n_queries test frames at once, on the device: for every query the ring positions are
+ * visited as the reference does (start below currentArrayId, step down with wrap-around, stop at the first position outside the
+ * match window or at an invalid entry), candidates need frameId gap > min_match_difference (util::MIN_MATCH_DIFFERENCE = 8), and
+ * those passing the histogram / view-angle test (ellc_lc_gate's statistics) become ellc_pair records -- keyframe = the loop frame's
+ * kf_slot, frame = the test frame's slot, flags = pair_flags, init_pose = log(exp(test pose) exp(loop pose)^-1) as
+ * GetImagePoseEstimate derives it for a loop-closure call (src/GlobalOptimize.cpp:560-568, src/ImageFunc.cpp:97-108) -- compacted
+ * query-major, walk order inside a query.  The list stays on the device for ellc_track_generated_pairs; *n_pairs and, if not NULL,
+ * pairs / stats / query_of_pair (capacity n_queries * ring_len each; stats[k].reserved = ring position of the matched loop frame)
+ * are copied to the host.  ring_len <= 64 (the reference: MAX_LOOP_ARRAY_LENGTH_SCALE_AVG = 43). */
+int ellc_lc_generate_pairs(ellc_handle* h, int32_t ring_len, const ellc_lc_ring_entry* ring, int32_t n_queries, const ellc_lc_query* queries,
+                           int32_t min_match_difference, float match_threshold, float max_rel_view_angle, int32_t pair_flags,
+                           int32_t* n_pairs, ellc_pair* pairs, ellc_lc_stats* stats, int32_t* query_of_pair);
+/* Track the list the last ellc_lc_generate_pairs left on the device (n_pairs as it reported) without sending it back: the pair
+ * records never leave the GPU.  results: HOST array of n_pairs records. */
+int ellc_track_generated_pairs(ellc_handle* h, int32_t n_pairs, ellc_result* results);
 
 int ellc_frame_image_devptr(ellc_handle* h, int32_t frame_slot, uint8_t** image);
 int ellc_keyframe_devptrs(ellc_handle* h, int32_t kf_slot, uint8_t** image, float** depth, float** var,
