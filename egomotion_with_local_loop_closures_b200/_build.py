@@ -43,5 +43,18 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_variant(name, defines):
+    """EXPERIMENTS: the library with extra -D flags as build/variants/libellc_gn_<name>.so (select it with ELLC_LIB=...)."""
+    out_dir = os.path.join(os.path.dirname(PKG), "build", "variants")
+    os.makedirs(out_dir, exist_ok=True)
+    out = os.path.join(out_dir, "libellc_gn_%s.so" % name)
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + ["-DELLC_SRC_HASH=\"%s+%s\"" % (source_hash(), name)] + ["-D" + d for d in defines] + ["-o", out] + SOURCES
+    proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + proc.stdout + proc.stderr)
+    return out
+
+
 if __name__ == "__main__":
     print(build(force=True, verbose=True))

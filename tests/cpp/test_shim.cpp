@@ -139,7 +139,8 @@ int main(int argc, char** argv) {
             for (int i = 0; i < pw.nRows * pw.nCols; ++i) cs += fr[0]->weight_pyramid[L].ptr<float>(0)[i];
             printf("pw_scatter %.9g\n", cs);
             // (c) inverse-compositional constant-weight iterations through the class (weights = what saveWeights left, finalised)
-            kf.finaliseWeights();
+            kf.finaliseWeights();                            // (prints the reference's "Weights cannot be averaged" for the empty levels)
+            printf("\n");
             float lpose[6] = {0, 0, 0, 0, 0, 0};
             PixelWisePyramid pl(&kf, fr[1], lpose, &dm);
             pl.pose = lpose;
@@ -195,9 +196,11 @@ int main(int argc, char** argv) {
                 std::vector<frame*> copies, kfs; std::vector<depthMap*> dms; std::vector<float> inits;
                 for (int i = 0; i < 70; ++i) { copies.push_back(new frame(*fr[i % n])); kfs.push_back(&kf); dms.push_back(&dm); for (int k = 0; k < 6; ++k) inits.push_back(0.f); }
                 std::vector<float> out = ellc_host::TrackPairsBatched(kfs, dms, copies, inits);
-                int nb = 0;
-                for (int i = 0; i < 70; ++i) for (int k = 0; k < 6; ++k) nb += out[i * 6 + k] != want[i % n][k];
-                printf("bigbatch %d\n", nb);
+                // (the 64-pair sub-batch runs with 4 CTAs per pair, a pair alone with 8: another summation tree, so the poses agree to
+                // rounding, not bit for bit; a recycled slot would show up as a pose of another frame, 1e-3 away)
+                double worst = 0;
+                for (int i = 0; i < 70; ++i) for (int k = 0; k < 6; ++k) worst = std::max(worst, (double)std::fabs(out[i * 6 + k] - want[i % n][k]));
+                printf("bigbatch %.3g\n", worst);
                 for (frame* c : copies) delete c;
             }
             for (frame* c : fr) delete c;

@@ -207,7 +207,7 @@ def test_shim_class_surface(tmp_path, oracle_mod):
     blob = tmp_path / "case.bin"
     _write_blob(blob, w, h, k, kf, frames)
     out = subprocess.check_output([exe, str(blob), "--surface"], text=True)
-    lines = [l.split() for l in out.strip().splitlines()]
+    lines = [l.split() for l in out.strip().splitlines() if l.strip()]
     get = lambda tag: [l for l in lines if l[0] == tag]
     L = 1
     ocfg = oracle_config(oracle_mod, dict(width=w, height=h))
@@ -293,4 +293,4 @@ def test_shim_class_surface(tmp_path, oracle_mod):
     # (f) two threads, two contexts, bit-identical poses; (g) oversized batch split without overwriting slots
     t = get("threads")[0]
     assert t[1] == "0" and t[2] == "0" and int(t[4]) >= 3, t
-    assert get("bigbatch")[0][1] == "0"
+    assert float(get("bigbatch")[0][1]) < 1e-6
