@@ -552,6 +552,8 @@ def main():
         kernel_ms.append(trk.last_track_kernel_ms())
         return out
 
+    per_rank_ms = []                                           # per timed region: every rank's own ms per step (diagnostic)
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -591,8 +593,10 @@ def main():
         clocks = clk.stop() if clk else None
         if world > 1:
             t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+            allt = torch.zeros(world, dtype=torch.float64, device="cuda")
+            dist.all_gather_into_tensor(allt, t)
+            per_rank_ms.append([float(v) / steps for v in allt.cpu().tolist()])
+            ms = float(allt.max().item())
         return ms, res, launches, clocks
 
     pipelined = (not lc) and n_pairs >= 148
@@ -605,6 +609,11 @@ def main():
         own = trk.track_batch(pairs)
     res = own
     k_ms = float(np.mean(kernel_ms)) if kernel_ms else ms / args.steps
+    per_rank_kernel_ms = None
+    if world > 1:
+        kt = torch.zeros(world, dtype=torch.float64, device="cuda")
+        dist.all_gather_into_tensor(kt, torch.tensor([k_ms], dtype=torch.float64, device="cuda"))
+        per_rank_kernel_ms = [float(v) for v in kt.cpu().tolist()]
     value = n_total * args.steps / (ms * 1e-3)
     alg = algorithmic_bytes(res)
     pix_it = pixel_iterations(res)
@@ -729,6 +738,10 @@ def main():
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
         if n_pairs == 1:
             line["latency_ms_per_track"] = ms / args.steps
+        if world > 1:
+            line["per_rank"] = {"ms_per_step": per_rank_ms[0] if per_rank_ms else None, "kernel_ms_per_launch": per_rank_kernel_ms,
+                                "e2e_ms_per_step": per_rank_ms[1] if len(per_rank_ms) > 1 else None,
+                                "note": "every rank tracks its own seeded segment: iteration counts, hence kernel times, differ a little between ranks"}
         emit(line)
     trk.close()
     if world > 1:

@@ -31,12 +31,18 @@ using namespace ellc;
 // Token t (the t-th exchanged batch, the same number on every rank) uses table t % kXchgRing everywhere.  A sender's tracking
 // kernel stores its records into the tables of the receiving ranks (peer memory mapped with CUDA IPC or, inside one process,
 // cudaDeviceEnablePeerAccess) and a one-warp kernel behind it adds its record count to the receivers' arrived[] counters; a
-// receiver's HOST polls its own counter, copies the table out and publishes released[] = t, which a sender reads (from the
+// receiver's HOST polls its own counter, copies the table out and publishes released[0] = t, which a sender reads (from the
 // receiver's memory) before it reuses that table for token t + kXchgRing.  No kernel ever spins.
+// The release is published by a one-thread kernel on the receiver's TRACKING stream, in front of its next batch (or at once
+// when no batch is queued).  Measured at N = 2: the same kernel on the download stream has to find a free CTA slot among the
+// pending CTAs of the highest-priority tracking kernel (the receiving rank lost 0.5-0.8 ms per step and its e2e uploads could
+// not overlap the running batch); an 8-byte cudaMemcpyAsync into the block instead waits for the whole running kernel (25 ms
+// per step instead of 14).  At a batch boundary the GPU is free and the release costs nothing.
 constexpr int kXchgRing = 4;
 struct XchgHeader {
     unsigned long long arrived[kXchgRing];             // records delivered into table r, cumulative over the tokens that used it
-    unsigned long long released[kXchgRing];            // last token whose table r the owner has finished copying out
+    unsigned long long released[kXchgRing];            // [0]: last token whose table the owner has finished copying out (tokens are
+                                                       // consumed in order); [1..]: unused
     unsigned long long pad[32 - 2 * kXchgRing];
 };
 static_assert(sizeof(XchgHeader) == 256, "exchange header is one 256-byte record");
@@ -51,6 +57,7 @@ struct ellc_exchange {
     struct Tok { long long seq; int n, n_total, root; } tok[kXchgRing];
     unsigned long long** d_ctr;                        // device array [kXchgRing][ELLC_MAX_RANKS]: &header(d)->arrived[r]
     unsigned long long* h_poll;                        // pinned scratch of the host polls
+    long long consumed, published;                     // last token copied out by this rank / last one written to released[0]
 };
 struct ellc_handle {
     ellc_config cfg;
@@ -555,6 +562,15 @@ static int validate_pairs(ellc_handle* h, int n, const ellc_pair* pairs) {
     return ELLC_OK;
 }
 
+static int xchg_publish(ellc_handle* h, cudaStream_t st) {
+    ellc_exchange* xc = h->xc;
+    if (!xc || !xc->attached || xc->consumed <= xc->published) return ELLC_OK;
+    h->launches += launch_xchg_store(st, &reinterpret_cast<XchgHeader*>(xc->block)->released[0], (unsigned long long)xc->consumed);
+    CU_TRY(h, cudaGetLastError());
+    xc->published = xc->consumed;
+    return ELLC_OK;
+}
+
 // Launch parameters of the optional result exchange of a batch (ellc_track_batch_exchange)
 struct XchgLaunch {
     int n_dst = 0;
@@ -629,6 +645,8 @@ static int track_launch(ellc_handle* h, int n, const ellc_pair* pairs, bool want
     CU_TRY(h, cudaStreamWaitEvent(ts, h->main_ev, 0));
     const bool serial = !h->overlap_batches || want_trace || save_weights || n_fwd < n;
     if (serial && seq > 1 && seq - 1 > h->batch_done_seq) CU_TRY(h, cudaStreamWaitEvent(ts, h->batch_ev[(seq - 1) & 3], 0));
+    rc = xchg_publish(h, ts);                              // tables this rank has copied out since its last batch: tell the senders
+    if (rc) return rc;
     if (!dev) {
         rc = stage_h2d_on(h, ts, h->d_pairs, pairs, (size_t)n * sizeof(ellc_pair));
         if (rc) return rc;
@@ -1574,7 +1592,7 @@ int ellc_track_batch_exchange(ellc_handle* h, int32_t n, const ellc_pair* pairs,
     for (int d = d0; d < d1; ++d) {
         // flow control: receiver d has copied out the token that used this table last
         if (t > kXchgRing) {
-            int rc = xchg_poll_until(h, &xchg_header(xc, d)->released[r], (unsigned long long)(t - kXchgRing), 20.0, "a receiver to release its table");
+            int rc = xchg_poll_until(h, &xchg_header(xc, d)->released[0], (unsigned long long)(t - kXchgRing), 20.0, "a receiver to release its table");
             if (rc) return rc;
         }
         xl.dst[xl.n_dst++] = xchg_table(xc, d, r);
@@ -1605,8 +1623,12 @@ int ellc_exchange_wait(ellc_handle* h, int64_t token, ellc_result* results) {
     int rc = xchg_poll_until(h, &xchg_header(xc, xc->rank)->arrived[r], xc->expected[r], 30.0, "the records of all ranks");
     if (rc) return rc;
     if (results) CU_TRY(h, cudaMemcpyAsync(results, xchg_table(xc, xc->rank, r), (size_t)tk.n_total * sizeof(ellc_result), cudaMemcpyDeviceToHost, h->d2h_stream));
-    h->launches += launch_xchg_store(h->d2h_stream, &xchg_header(xc, xc->rank)->released[r], (unsigned long long)token);
-    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaStreamSynchronize(h->d2h_stream));
+    xc->consumed = token;
+    if (h->batch_seq == tk.seq) {                          // nothing queued behind this batch: the GPU is idle, publish now
+        rc = xchg_publish(h, h->d2h_stream);
+        if (rc) return rc;
+    }
     CU_TRY(h, cudaStreamSynchronize(h->d2h_stream));
     return ELLC_OK;
 }

@@ -46,7 +46,7 @@ int launch_pull_host(cudaStream_t st, void* dst, const void* src_host_devptr, si
 int launch_track(cudaStream_t st, const TrackParams& p, int cluster, bool strict);
 // loop-closure (inverse-compositional constant-weight) variant: one CTA per pair, pairs = p.order[0 .. p.n_pairs)
 int launch_track_lc(cudaStream_t st, const TrackParams& p, bool strict);
-// result exchange: thread d adds n_records to *d_counters[d] (system scope); store a value to a counter (system scope)
+// result exchange: thread d adds n_records to *d_counters[d] (system scope)
 int launch_xchg_signal(cudaStream_t st, unsigned long long* const* d_counters, int n_dst, unsigned long long n_records);
 int launch_xchg_store(cudaStream_t st, unsigned long long* d_counter, unsigned long long value);
 // single-thread kernel running solve_update_f on the device (ellc_solve_update)
