@@ -301,7 +301,8 @@ def main():
     ap.add_argument("--frames", type=int, default=None, help="frames per GPU per step")
     ap.add_argument("--pairs-per-frame", type=int, default=None, help="1 sequential + K=8 loop-closure candidates")
     ap.add_argument("--arith", default="fast", choices=["fast", "strict"])
-    ap.add_argument("--cluster", type=int, default=0)
+    ap.add_argument("--cluster", type=int, default=0, help="CTAs per pair (thread-block cluster): 0 = the library chooses from the batch size")
+    ap.add_argument("--pairs-per-cta", type=int, default=0, help="pairs one CTA tracks in lockstep: 0 = the library chooses")
     ap.add_argument("--lc-mode", default="forward", choices=["forward", "const_weight"],
                     help="const_weight: the K-1 loop-closure pairs of every frame run the reference's constant-weight "
                          "inverse-compositional tracker (FLAG_DO_CONST_WEIGHT_POSE_ESTIMATION); not the headline workload")
@@ -351,7 +352,7 @@ def main():
     cfg = capi.default_config(W, H, fx=float(k["fx"]), fy=float(k["fy"]), cx=float(k["cx"]), cy=float(k["cy"]),
                               max_keyframes=2 * args.keyframes, max_frames=2 * args.frames, device=local_rank,
                               arithmetic=capi.ARITH_STRICT if args.arith == "strict" else capi.ARITH_FAST,
-                              ctas_per_pair=args.cluster)
+                              ctas_per_pair=args.cluster, pairs_per_cta=args.pairs_per_cta)
     trk = capi.Tracker(cfg)
     stream = torch.cuda.ExternalStream(trk.stream(), device=torch.device("cuda", local_rank))
 
@@ -727,7 +728,7 @@ def main():
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": conf["workload"] + ("_lc_const_weight" if lc else ""), "width": W, "height": H, "keyframes_per_gpu": args.keyframes,
                            "frames_per_gpu": args.frames, "pairs_per_gpu_per_step": n_pairs, "pairs_per_frame": args.pairs_per_frame,
-                           "arithmetic": args.arith, "library": lib_version,
+                           "arithmetic": args.arith, "ctas_per_pair": args.cluster or "auto", "pairs_per_cta": args.pairs_per_cta or "auto", "library": lib_version,
                            "pipelining": ("resident inputs held twice; steps alternate between the two sets of slots: preparation of step k+1 on a "
                                           "low-priority stream overlaps the tracking kernel of step k, records of step k fetched during step k+1" if pipelined else
                                           "none (one set of slots; every step prepares, tracks and reads back before the next one starts)"),

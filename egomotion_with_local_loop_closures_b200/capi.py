@@ -73,7 +73,7 @@ SYMBOLS = ["ellc_default_config", "ellc_create", "ellc_destroy", "ellc_last_erro
            "ellc_results_download",
            "ellc_synchronize", "ellc_gn_evaluate", "ellc_solve_update", "ellc_solve_update_rt", "ellc_read_frame_level",
            "ellc_read_keyframe_level", "ellc_level_dims", "ellc_concat_relative", "ellc_concat_origin",
-           "ellc_se3_exp", "ellc_launch_count", "ellc_reset_launch_count", "ellc_stream", "ellc_stream_of", "ellc_selftest_division", "ellc_reset_keyframe_weights", "ellc_accumulate_weights",
+           "ellc_se3_exp", "ellc_launch_count", "ellc_reset_launch_count", "ellc_stream", "ellc_stream_of", "ellc_selftest_division", "ellc_selftest_unzero", "ellc_reset_keyframe_weights", "ellc_accumulate_weights",
            "ellc_finalise_weights", "ellc_upload_keyframe_weights", "ellc_read_keyframe_weights", "ellc_read_frame_weights",
            "ellc_prepare_keyframes_lc", "ellc_frame_histograms", "ellc_lc_gate", "ellc_upload_keyframe_hypotheses", "ellc_read_keyframe_occupancy", "ellc_read_keyframe_depth", "ellc_last_track_kernel_ms",
            "ellc_prepare_async", "ellc_batch_kernel_ms", "ellc_batch_interval_ms", "ellc_fence",
@@ -142,6 +142,7 @@ def lib():
         L.ellc_frame_histograms.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         L.ellc_lc_gate.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_float, C.c_float, C.c_void_p]
         L.ellc_selftest_division.argtypes = [C.c_void_p, C.c_int64, C.c_uint64, C.POINTER(C.c_int64)]
+        L.ellc_selftest_unzero.argtypes = [C.c_void_p, C.c_int64, C.c_uint64, C.POINTER(C.c_int64)]
         L.ellc_stream_of.restype = C.c_void_p
         L.ellc_stream_of.argtypes = [C.c_void_p, C.c_int32]
         L.ellc_last_track_kernel_ms.restype = C.c_float
@@ -503,6 +504,11 @@ class Tracker:
         out = (C.c_int64 * 2)()
         self._chk(lib().ellc_selftest_division(self._h, int(n), int(seed), out))
         return int(out[0]), int(out[1])
+
+    def selftest_unzero(self, n, seed=1):
+        out = C.c_int64(0)
+        self._chk(lib().ellc_selftest_unzero(self._h, int(n), int(seed), C.byref(out)))
+        return int(out.value)
 
     def stream_of(self, which):
         return lib().ellc_stream_of(self._h, which)

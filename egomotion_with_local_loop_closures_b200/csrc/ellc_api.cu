@@ -1408,6 +1408,19 @@ int ellc_selftest_division(ellc_handle* h, int64_t n, uint64_t seed, int64_t mis
     mismatches[0] = (int64_t)out[0]; mismatches[1] = (int64_t)out[1];
     return ELLC_OK;
 }
+int ellc_selftest_unzero(ellc_handle* h, int64_t n, uint64_t seed, int64_t* mismatches) {
+    if (!h) return ELLC_ERR_INVALID;
+    if (n < 0 || !mismatches) { h->err = "bad self-test arguments"; return ELLC_ERR_INVALID; }
+    CU_TRY(h, cudaSetDevice(h->cfg.device));
+    unsigned long long* d = reinterpret_cast<unsigned long long*>(h->d_small);
+    CU_TRY(h, cudaMemsetAsync(d, 0, sizeof(unsigned long long), h->stream));
+    h->launches += launch_unzero_selftest(h->stream, (long long)n, (unsigned long long)seed, d);
+    unsigned long long out = 0;
+    CU_TRY(h, cudaMemcpyAsync(&out, d, sizeof(out), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    *mismatches = (int64_t)out;
+    return ELLC_OK;
+}
 void* ellc_stream_of(ellc_handle* h, int32_t which) {
     if (!h) return nullptr;
     return which == 1 ? (void*)h->copy_stream : which == 2 ? (void*)h->d2h_stream : which == 3 ? (void*)h->tstream[0]

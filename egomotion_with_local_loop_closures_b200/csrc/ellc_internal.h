@@ -52,6 +52,7 @@ int launch_xchg_store(cudaStream_t st, unsigned long long* d_counter, unsigned l
 // single-thread kernel running solve_update_f on the device (ellc_solve_update)
 // div2_rn_shared (the pixel loop's shared-reciprocal exact division) against __fdiv_rn on n pseudo-random operand triples
 int launch_div_selftest(cudaStream_t st, long long n, unsigned long long seed, unsigned long long* d_counts /*[2]*/);
+int launch_unzero_selftest(cudaStream_t st, long long n, unsigned long long seed, unsigned long long* d_counts /*[1]*/);
 int launch_invert6(cudaStream_t st, const float* d_in /*H36*/, float* d_out /*Hinv36 ok1*/);
 int launch_solve_update(cudaStream_t st, const float* d_in /*H36 b6 pose6 weight6*/, float* d_out /*pose6 delta6 wp1 ok1 rt12 small1*/, int fast);
 

@@ -377,6 +377,10 @@ void*   ellc_stream(ellc_handle* h);
  * src/PixelWisePyramid.cpp:250-251) against __fdiv_rn on n pseudo-random operand triples; mismatches[0]: quotients with a normal
  * result that differ, mismatches[1]: differing quotients below 2^-120. */
 int ellc_selftest_division(ellc_handle* h, int64_t n, uint64_t seed, int64_t mismatches[2]);
+/* Self-test of the GN kernel's UNZERO (src/ExternVariable.h:232, applied to Z' at src/PixelWisePyramid.cpp:246): the fast
+ * flavour's three-instruction form against the macro's two comparisons on 64 special values and n pseudo-random bit patterns;
+ * *mismatches = inputs whose results differ (two NaNs count as equal). */
+int ellc_selftest_unzero(ellc_handle* h, int64_t n, uint64_t seed, int64_t* mismatches);
 /* which: 0 = main compute stream (same as ellc_stream), 1 = H2D upload stream, 2 = D2H result stream, 3 / 4 = the two tracking streams (diagnostics). */
 void*   ellc_stream_of(ellc_handle* h, int32_t which);
 /* device time of the track kernel(s) of the most recent ellc_track_batch* call, in milliseconds (CUDA events) */

@@ -96,7 +96,26 @@ def rare_blocks(ins, lo, hi):
             if m:
                 tgt = addr_index.get(int(m.group(1), 16))
                 if tgt is not None and i < tgt <= hi:
+                    prev = ins[tgt - 1][1]
+                    if not prev.startswith("@") and opcode(prev) == "BRA":
+                        continue                                    # layout 2 below: this branch jumps TO the rare block
                     skipped.update(range(i + 1, tgt))
+    # the other layout of the same thing: `@!P BRA slow; <usual path>; BRA join; slow: ...; join:` -- the block between an
+    # unconditional forward BRA and its target is rare when a conditional branch of the loop jumps to its first instruction
+    cond_targets = set()
+    for i in range(lo, hi + 1):
+        a, t = ins[i]
+        if t.startswith("@") and opcode(t).startswith("BRA"):
+            m = re.search(r"0x([0-9a-f]+)", t)
+            if m and int(m.group(1), 16) in addr_index:
+                cond_targets.add(addr_index[int(m.group(1), 16)])
+    for i in range(lo, hi + 1):
+        a, t = ins[i]
+        if not t.startswith("@") and opcode(t) == "BRA":
+            m = re.search(r"0x([0-9a-f]+)", t)
+            tgt = addr_index.get(int(m.group(1), 16)) if m else None
+            if tgt is not None and i + 1 < tgt <= hi and (i + 1) in cond_targets:
+                skipped.update(range(i + 1, tgt))
     return skipped
 
 
