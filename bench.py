@@ -20,6 +20,7 @@ Timed regions
 Inputs (hundreds of MB per step) are larger than the 126 MB L2, so no explicit L2 flush is needed between steps.
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -436,7 +437,7 @@ def main():
     primary = (wl["kf_idx"] == (wl["fr_idx"] % args.keyframes))
     flags = np.where(primary, capi.PAIR_SAVE_WEIGHTS, capi.PAIR_CONST_WEIGHT).astype(np.int32) if lc else 0
     pairs = trk.make_pairs(wl["kf_idx"], wl["fr_idx"], wl["init"], flags=flags)
-    pairs_half = [pairs, trk.make_pairs(wl["kf_idx"] + args.keyframes, wl["fr_idx"] + args.frames, wl["init"])]
+    pairs_half = [pairs, trk.make_pairs(wl["kf_idx"] + args.keyframes, wl["fr_idx"] + args.frames, wl["init"], flags=flags)]
     if lc:
         args.no_e2e = True                                     # an upload invalidates the loop-closure records: resident mode only
         args.no_cpu_baseline = True                            # (the forward CPU baseline is not this workload)
@@ -444,21 +445,22 @@ def main():
     kf_slots = np.arange(args.keyframes, dtype=np.int32)
 
     upload_all()
-    if not lc:
-        upload_all(1)                                          # the forward workload is resident twice: steps alternate between the halves
+    upload_all(1)                                              # the workload is resident twice: steps alternate between the halves
     trk.synchronize()
     if lc:
         # untimed setup, as in the reference's flow: every keyframe's weight pyramid = average of the last-iteration weights of
-        # the sequential tracks of its frames (saveWeights / finaliseWeights), then the loop-closure records
-        seq = trk.make_pairs(wl["kf_idx"][primary], wl["fr_idx"][primary], wl["init"][primary], flags=capi.PAIR_SAVE_WEIGHTS)
-        trk.track_batch(seq)
-        for kslot in range(args.keyframes):
-            trk.reset_keyframe_weights(kslot)
-            fr = np.sort(wl["fr_idx"][primary][wl["kf_idx"][primary] == kslot])
-            for lo in range(0, len(fr), 64):
-                trk.accumulate_weights(kslot, fr[lo:lo + 64])
-            trk.finalise_weights(kslot)
-        trk.prepare_keyframes_lc(np.arange(args.keyframes, dtype=np.int32))
+        # the sequential tracks of its frames (saveWeights / finaliseWeights), then the loop-closure records -- for both halves
+        for half in (0, 1):
+            ko, fo = half * args.keyframes, half * args.frames
+            seq = trk.make_pairs(wl["kf_idx"][primary] + ko, wl["fr_idx"][primary] + fo, wl["init"][primary], flags=capi.PAIR_SAVE_WEIGHTS)
+            trk.track_batch(seq)
+            for kslot in range(args.keyframes):
+                trk.reset_keyframe_weights(ko + kslot)
+                fr = np.sort(wl["fr_idx"][primary][wl["kf_idx"][primary] == kslot])
+                for lo in range(0, len(fr), 64):
+                    trk.accumulate_weights(ko + kslot, fo + fr[lo:lo + 64])
+                trk.finalise_weights(ko + kslot)
+            trk.prepare_keyframes_lc(np.arange(args.keyframes, dtype=np.int32) + ko)
         trk.synchronize()
     setup_s = time.time() - t_setup
 
@@ -524,14 +526,19 @@ def main():
             upload_all(half)
         else:
             trk.prepare_async(fr_slots + half * args.frames, kf_slots + half * args.keyframes)
+            if lc:
+                trk.prepare_keyframes_lc_async(kf_slots + half * args.keyframes)   # the per-keyframe Jacobians / hessians are part of the step
         t1 = time.perf_counter()
         ticket = launch(pairs_half[half])
         pipe["launched"] += 1
+        host_ms["enqueue"].append(1e3 * (time.perf_counter() - t0))
         if e2e:
             pipe["host_upload_ms"] = pipe.get("host_upload_ms", 0.0) + 1e3 * (t1 - t0)
             pipe["host_launch_ms"] = pipe.get("host_launch_ms", 0.0) + 1e3 * (time.perf_counter() - t1)
         if pipe["pending"] is not None:
+            t2 = time.perf_counter()
             pipe["last"] = fetch(pipe["pending"])
+            host_ms["fetch"].append(1e3 * (time.perf_counter() - t2))
             if not e2e and pipe["launched"] >= (3 if overlap else 2):
                 note_kernel_time()
         pipe["pending"] = ticket
@@ -554,6 +561,7 @@ def main():
         return out
 
     per_rank_ms = []                                           # per timed region: every rank's own ms per step (diagnostic)
+    host_ms = {"enqueue": [], "fetch": []}                     # host time of the two halves of a pipelined step (diagnostic)
 
     def barrier():
         if world > 1:
@@ -572,8 +580,13 @@ def main():
             res = r2 if r2 is not None else res
         barrier()
         kernel_ms.clear()
+        host_ms["enqueue"].clear(); host_ms["fetch"].clear()
         pipe["launched"] = 0
         trk.reset_launch_count()
+        # the host enqueues one step ahead of the GPU: a collector pause longer than a step would idle the device.  Collect now,
+        # keep the collector off inside the timed region (its allocations are a few result arrays per step).
+        gc.collect()
+        gc.disable()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         if clk:
             clk.mark_begin()
@@ -587,6 +600,7 @@ def main():
         stream.wait_stream(torch.cuda.current_stream())   # ... and anything issued on torch's stream
         e1.record(stream)
         barrier()
+        gc.enable()
         if clk:
             clk.mark_end()
         ms = e0.elapsed_time(e1)
@@ -600,11 +614,12 @@ def main():
             ms = float(allt.max().item())
         return ms, res, launches, clocks
 
-    pipelined = (not lc) and n_pairs >= 148
+    pipelined = n_pairs >= 148
     if pipelined:
         ms, res2, launches, clocks = timed(step_pipelined, args.steps, args.warmup, sample_clocks=True, drain=drain_pipelined)
     else:
         ms, res2, launches, clocks = timed(step_resident, args.steps, args.warmup, sample_clocks=True)
+    host_diag = {k: {"median": float(np.median(v)), "max": float(np.max(v))} for k, v in host_ms.items() if v}
     own, table = res2 if res2 is not None else (None, None)
     if own is None:                                            # a rank that receives nothing still needs its own counters for the roofline
         own = trk.track_batch(pairs)
@@ -739,6 +754,10 @@ def main():
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
         if n_pairs == 1:
             line["latency_ms_per_track"] = ms / args.steps
+        if host_diag:
+            line["host_ms_per_step"] = dict(host_diag, note="host time of the two halves of a pipelined step on rank 0: enqueue (prepare + launch) and "
+                                                                "fetch (blocks until the previous step's records are on the host); a max far above the median "
+                                                                "is a host stall that can idle the GPU (the collector is off inside the timed region)")
         if world > 1:
             line["per_rank"] = {"ms_per_step": per_rank_ms[0] if per_rank_ms else None, "kernel_ms_per_launch": per_rank_kernel_ms,
                                 "e2e_ms_per_step": per_rank_ms[1] if len(per_rank_ms) > 1 else None,

@@ -75,7 +75,7 @@ SYMBOLS = ["ellc_default_config", "ellc_create", "ellc_destroy", "ellc_last_erro
            "ellc_read_keyframe_level", "ellc_level_dims", "ellc_concat_relative", "ellc_concat_origin",
            "ellc_se3_exp", "ellc_launch_count", "ellc_reset_launch_count", "ellc_stream", "ellc_stream_of", "ellc_selftest_division", "ellc_selftest_unzero", "ellc_reset_keyframe_weights", "ellc_accumulate_weights",
            "ellc_finalise_weights", "ellc_upload_keyframe_weights", "ellc_read_keyframe_weights", "ellc_read_frame_weights",
-           "ellc_prepare_keyframes_lc", "ellc_frame_histograms", "ellc_lc_gate", "ellc_upload_keyframe_hypotheses", "ellc_read_keyframe_occupancy", "ellc_read_keyframe_depth", "ellc_last_track_kernel_ms",
+           "ellc_prepare_keyframes_lc", "ellc_prepare_keyframes_lc_async", "ellc_frame_histograms", "ellc_lc_gate", "ellc_upload_keyframe_hypotheses", "ellc_read_keyframe_occupancy", "ellc_read_keyframe_depth", "ellc_last_track_kernel_ms",
            "ellc_prepare_async", "ellc_batch_kernel_ms", "ellc_batch_interval_ms", "ellc_fence",
            "ellc_exchange_create", "ellc_exchange_attach_ipc", "ellc_exchange_attach_local", "ellc_track_batch_exchange",
            "ellc_exchange_wait", "ellc_exchange_destroy", "ellc_se3_exp_closed", "ellc_se3_log_closed",
@@ -136,6 +136,7 @@ def lib():
         L.ellc_read_keyframe_weights.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_int32)]
         L.ellc_read_frame_weights.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
         L.ellc_prepare_keyframes_lc.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        L.ellc_prepare_keyframes_lc_async.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.ellc_upload_keyframe_hypotheses.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 5
         L.ellc_read_keyframe_occupancy.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_float)]
         L.ellc_read_keyframe_depth.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
@@ -499,6 +500,10 @@ class Tracker:
     def prepare_keyframes_lc(self, kf_slots):
         ks = np.ascontiguousarray(kf_slots, np.int32)
         self._chk(lib().ellc_prepare_keyframes_lc(self._h, len(ks), _p(ks)))
+
+    def prepare_keyframes_lc_async(self, kf_slots):
+        ks = np.ascontiguousarray(kf_slots, np.int32)
+        self._chk(lib().ellc_prepare_keyframes_lc_async(self._h, len(ks), _p(ks)))
 
     def selftest_division(self, n, seed=1):
         out = (C.c_int64 * 2)()

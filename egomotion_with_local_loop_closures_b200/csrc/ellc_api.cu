@@ -1395,6 +1395,39 @@ int ellc_prepare_keyframes_lc(ellc_handle* h, int32_t n, const int32_t* kf_slots
     return ELLC_OK;
 }
 
+// The pipelined form (see ellc_prepare_async): on the low-priority preparation stream, behind the last batch that read these
+// keyframe slots only, so that it overlaps the batch that is tracking now.
+int ellc_prepare_keyframes_lc_async(ellc_handle* h, int32_t n, const int32_t* kf_slots) {
+    if (!h) return ELLC_ERR_INVALID;
+    if (n < 0 || (n > 0 && !kf_slots) || n > h->slots_cap) { h->err = "bad keyframe slot list"; return ELLC_ERR_INVALID; }
+    long long reader = 0;
+    for (int i = 0; i < n; ++i) {
+        int rc = check_kf(h, kf_slots[i]);
+        if (rc) return rc;
+        if (h->kf_state[kf_slots[i]] != 2) { h->err = "keyframe slot not prepared (ellc_prepare_async / ellc_prepare_keyframes first)"; return ELLC_ERR_NOT_READY; }
+        reader = std::max(reader, h->kf_reader[kf_slots[i]]);
+    }
+    if (n == 0) return ELLC_OK;
+    CU_TRY(h, cudaSetDevice(h->cfg.device));
+    int rc = ensure_lc_pools(h);
+    if (rc) return rc;
+    // weights written on the main stream (accumulate / finalise / upload) are ordered in front of the preparation stream
+    CU_TRY(h, cudaEventRecord(h->main_ev, h->stream));
+    CU_TRY(h, cudaStreamWaitEvent(h->prep_stream, h->main_ev, 0));
+    if (reader > h->batch_done_seq && reader + 4 > h->batch_seq)
+        CU_TRY(h, cudaStreamWaitEvent(h->prep_stream, h->batch_ev[reader & 3], 0));
+    int* d_slots = h->d_slots_p + h->slots_cap;
+    rc = stage_h2d_on(h, h->prep_stream, d_slots, kf_slots, (size_t)n * sizeof(int));
+    if (rc) return rc;
+    h->launches += launch_lc_prepare(h->prep_stream, h->kf_geo, h->kf_pix, h->geo.win_off[kLevels], h->kf_count, h->kf_img, h->geo.img_off[kLevels],
+                                     h->kf_weight, h->kf_lc, h->kf_lcf, h->kf_lcp, h->kf_lcH, h->K, d_slots, n, h->geo);
+    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaEventRecord(h->prep_ev, h->prep_stream));
+    CU_TRY(h, cudaStreamWaitEvent(h->stream, h->prep_ev, 0));
+    for (int i = 0; i < n; ++i) h->kf_lc_ready[kf_slots[i]] = 1;
+    return ELLC_OK;
+}
+
 int ellc_selftest_division(ellc_handle* h, int64_t n, uint64_t seed, int64_t mismatches[2]) {
     if (!h) return ELLC_ERR_INVALID;
     if (n < 0 || !mismatches) { h->err = "bad self-test arguments"; return ELLC_ERR_INVALID; }

@@ -300,6 +300,11 @@ int ellc_read_keyframe_weights(ellc_handle* h, int32_t kf_slot, int32_t level, f
 int ellc_read_frame_weights(ellc_handle* h, int32_t frame_slot, int32_t level, float* weight);
 /* precomputePixelWiseInvCompositional + hessian (:561-680, :938) for the keyframes' current depth and weights. */
 int ellc_prepare_keyframes_lc(ellc_handle* h, int32_t n, const int32_t* kf_slots);
+/* The same on the pipelined preparation path of ellc_prepare_async: enqueued on the low-priority preparation stream, behind the weights
+ * written so far and behind the last batch that READ these keyframe slots only -- a caller that alternates between two sets of
+ * keyframe slots builds the loop-closure records of batch k+1 while batch k tracks.  The slots must be prepared
+ * (ellc_prepare_async / ellc_prepare_keyframes) and must not be in use by the batch in flight. */
+int ellc_prepare_keyframes_lc_async(ellc_handle* h, int32_t n, const int32_t* kf_slots);
 
 /* One evaluation of the normal equations at a given pose and level WITHOUT updating the pose: the body of
  * calculatePixelWiseParallel() up to src/PixelWisePyramid.cpp:442.  out->delta/pose_after/weighted_pose are left 0.
