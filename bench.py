@@ -176,19 +176,27 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
-    def _poll(self):
+    PERIOD_S = float(os.environ.get("ELLC_CLOCK_PERIOD_MS", "50")) * 1e-3
+
+    def _sample(self):
         nv, hd = self.nvml
-        while not self.stop_flag:
+        try:
+            mhz = float(nv.nvmlDeviceGetClockInfo(hd, nv.NVML_CLOCK_SM))
             try:
-                mhz = float(nv.nvmlDeviceGetClockInfo(hd, nv.NVML_CLOCK_SM))
-                try:
-                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(hd))
-                except Exception:
-                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(hd))
-                self.rows.append((time.perf_counter(), mhz, mask))
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(hd))
             except Exception:
-                pass
-            time.sleep(0.005)
+                mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(hd))
+            self.rows.append((time.perf_counter(), mhz, mask))
+        except Exception:
+            pass
+
+    def _poll(self):
+        # NVML queries go through the same driver as the CUDA calls of the benchmark loop: polled every 5 ms they coincided with
+        # sporadic 10-190 ms stalls of the loop's launches (host_ms_per_step.enqueue.max); 50 ms keeps >= 2 samples in any timed
+        # region of the default workload, and mark_begin / mark_end add one sample each while the device is under load.
+        while not self.stop_flag:
+            self._sample()
+            time.sleep(self.PERIOD_S)
 
     def _pump(self):
         for line in self.proc.stdout:
@@ -200,6 +208,11 @@ class ClockSampler:
     def mark_end(self):
         self.t1 = time.perf_counter()
 
+    def sample_now(self):
+        """One sample from the calling thread (bench: right after the last timed step has been enqueued, i.e. under load)."""
+        if self.nvml:
+            self._sample()
+
     def stop(self):
         self.stop_flag = True
         inside = lambda t: (self.t0 is None or t >= self.t0) and (self.t1 is None or t <= self.t1)
@@ -209,7 +222,7 @@ class ClockSampler:
             reasons = sorted({name for _, _, m in rows for bit, name in self.REASONS.items() if m & bit})
             sm = [r[1] for r in rows]
             return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "samples": len(sm), "reasons": reasons,
-                    "source": "nvml, 5 ms period, timed region only"}
+                    "source": "nvml, %.0f ms period + one sample with the last timed steps in flight, timed region only" % (1e3 * self.PERIOD_S)}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -508,14 +521,18 @@ def main():
     # Forward workload: steps alternate between two resident copies of the inputs (slot halves), so that the preparation of step
     # k+1 (pyramids, texels, selection lists: ellc_prepare_async, low-priority stream) overlaps the tracking kernel of step k, and
     # the records of step k are fetched while step k+1 runs.  Every step still does all of its own work.
-    pipe = {"k": 0, "pending": None, "last": None, "launched": 0}
+    # The host runs PIPE_DEPTH steps ahead of the records it fetches: while it waits for step k, steps k+1 .. k+PIPE_DEPTH are queued on
+    # the device.  (Depth 1 idles the GPU whenever the host loses more than one step's time between two launches -- measured: sporadic
+    # 10-50 ms gaps in the enqueue half of a step on the shared benchmark boxes, which cost up to 15 % of a 10-step run.)
+    PIPE_DEPTH = int(os.environ.get("ELLC_PIPE_DEPTH", "2"))
+    pipe = {"k": 0, "pending": [], "last": None, "launched": 0}
 
     overlap = os.environ.get("ELLC_OVERLAP") == "1"           # experiment: consecutive batches not serialised (measured slower)
 
     def note_kernel_time():
         # CUDA events around the tracking kernel of the batch just fetched, on its own stream.  (With ELLC_OVERLAP=1 the kernels of
         # consecutive batches run concurrently: then the completion-to-completion interval is the time a launch occupies the GPU.)
-        ms = trk.batch_interval_ms(1) if overlap else trk.batch_kernel_ms(1)
+        ms = trk.batch_interval_ms(PIPE_DEPTH) if overlap else trk.batch_kernel_ms(PIPE_DEPTH)
         if ms > 0:
             kernel_ms.append(ms)
 
@@ -531,24 +548,26 @@ def main():
         t1 = time.perf_counter()
         ticket = launch(pairs_half[half])
         pipe["launched"] += 1
-        host_ms["enqueue"].append(1e3 * (time.perf_counter() - t0))
+        t3 = time.perf_counter()
+        host_ms["enqueue"].append(1e3 * (t3 - t0))
+        host_ms["prepare"].append(1e3 * (t1 - t0))
+        host_ms["launch"].append(1e3 * (t3 - t1))
         if e2e:
             pipe["host_upload_ms"] = pipe.get("host_upload_ms", 0.0) + 1e3 * (t1 - t0)
             pipe["host_launch_ms"] = pipe.get("host_launch_ms", 0.0) + 1e3 * (time.perf_counter() - t1)
-        if pipe["pending"] is not None:
+        pipe["pending"].append(ticket)
+        if len(pipe["pending"]) > PIPE_DEPTH:
             t2 = time.perf_counter()
-            pipe["last"] = fetch(pipe["pending"])
+            pipe["last"] = fetch(pipe["pending"].pop(0))
             host_ms["fetch"].append(1e3 * (time.perf_counter() - t2))
-            if not e2e and pipe["launched"] >= (3 if overlap else 2):
+            if not e2e and pipe["launched"] >= PIPE_DEPTH + (2 if overlap else 1):
                 note_kernel_time()
-        pipe["pending"] = ticket
         pipe["k"] += 1
         return pipe["last"]
 
     def drain_pipelined():
-        if pipe["pending"] is not None:
-            pipe["last"] = fetch(pipe["pending"])
-            pipe["pending"] = None
+        while pipe["pending"]:
+            pipe["last"] = fetch(pipe["pending"].pop(0))
         return pipe["last"]
 
     def step_resident():                                       # loop-closure mode / single-pair latency: one set of slots, no pipelining
@@ -561,7 +580,7 @@ def main():
         return out
 
     per_rank_ms = []                                           # per timed region: every rank's own ms per step (diagnostic)
-    host_ms = {"enqueue": [], "fetch": []}                     # host time of the two halves of a pipelined step (diagnostic)
+    host_ms = {"enqueue": [], "fetch": [], "prepare": [], "launch": []}                     # host time of the two halves of a pipelined step (diagnostic)
 
     def barrier():
         if world > 1:
@@ -570,9 +589,15 @@ def main():
 
     def timed(fn, steps, warmup, sample_clocks=False, drain=None):
         res = None
-        clk = ClockSampler(local_rank) if sample_clocks else None
+        clk = ClockSampler(local_rank) if (sample_clocks and os.environ.get("ELLC_NO_CLOCKS") != "1") else None   # (diagnostic switch)
         if clk:
             clk.start()                                   # sampled over warm-up + timed steps (the same load)
+        # The Python collector stays off from here to the end of the timed region (its allocations are a few result arrays per
+        # step), and is run NOW, before the warm-up: anything slow between the synchronisation that opens the timed region and its
+        # first launch lets the device fall idle, and the first launch after an idle period was measured to block for 1 - 185 ms on
+        # the benchmark boxes (host_ms_per_step.launch: always step 0; profiles/r02_host_stalls.md).
+        gc.collect()
+        gc.disable()
         for _ in range(warmup):
             res = fn()
         if drain:
@@ -580,19 +605,18 @@ def main():
             res = r2 if r2 is not None else res
         barrier()
         kernel_ms.clear()
-        host_ms["enqueue"].clear(); host_ms["fetch"].clear()
+        for v in host_ms.values():
+            v.clear()
         pipe["launched"] = 0
         trk.reset_launch_count()
-        # the host enqueues one step ahead of the GPU: a collector pause longer than a step would idle the device.  Collect now,
-        # keep the collector off inside the timed region (its allocations are a few result arrays per step).
-        gc.collect()
-        gc.disable()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         if clk:
             clk.mark_begin()
         e0.record(stream)
         for _ in range(steps):
             res = fn()
+        if clk:
+            clk.sample_now()                              # the last steps are still running on the device
         if drain:
             r2 = drain()
             res = r2 if r2 is not None else res
@@ -619,7 +643,7 @@ def main():
         ms, res2, launches, clocks = timed(step_pipelined, args.steps, args.warmup, sample_clocks=True, drain=drain_pipelined)
     else:
         ms, res2, launches, clocks = timed(step_resident, args.steps, args.warmup, sample_clocks=True)
-    host_diag = {k: {"median": float(np.median(v)), "max": float(np.max(v))} for k, v in host_ms.items() if v}
+    host_diag = {k: {"median": float(np.median(v)), "max": float(np.max(v)), "argmax_step": int(np.argmax(v))} for k, v in host_ms.items() if v}
     own, table = res2 if res2 is not None else (None, None)
     if own is None:                                            # a rank that receives nothing still needs its own counters for the roofline
         own = trk.track_batch(pairs)
@@ -694,7 +718,7 @@ def main():
 
     e2e = None
     if not args.no_e2e and pipelined:
-        pipe.update({"k": 0, "pending": None, "last": None})
+        pipe.update({"k": 0, "pending": [], "last": None})
         ems, eres2, _, _ = timed(lambda: step_pipelined(e2e=True), args.steps, max(1, args.warmup), drain=drain_pipelined)
         e2e = {"value": n_total * args.steps / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes) * world,
                "d2h_bytes_per_step": int(d2h_bytes_job), "ms_per_step": ems / args.steps,
@@ -702,7 +726,7 @@ def main():
                                             "track_launch": pipe.get("host_launch_ms", 0.0) / max(1, pipe["k"])},
                "includes_gather": world > 1,
                "pipelining": "2 slot halves alternate; uploads of step k+1 on the copy stream overlap the kernels of step k; the records of step k "
-                             "(N>1: of ALL ranks, gathered on the receiving rank) are fetched during step k+1"}
+                             "(N>1: of ALL ranks, gathered on the receiving rank) are fetched during step k+2 (the host runs two steps ahead)"}
         if eres2 is not None and eres2[0] is not None:
             assert np.array_equal(eres2[0]["pose"], res["pose"]), "e2e and resident paths disagree"
     elif not args.no_e2e:
@@ -745,7 +769,7 @@ def main():
                            "frames_per_gpu": args.frames, "pairs_per_gpu_per_step": n_pairs, "pairs_per_frame": args.pairs_per_frame,
                            "arithmetic": args.arith, "ctas_per_pair": args.cluster or "auto", "pairs_per_cta": args.pairs_per_cta or "auto", "library": lib_version,
                            "pipelining": ("resident inputs held twice; steps alternate between the two sets of slots: preparation of step k+1 on a "
-                                          "low-priority stream overlaps the tracking kernel of step k, records of step k fetched during step k+1" if pipelined else
+                                          "low-priority stream overlaps the tracking kernel of step k, records of step k fetched during step k+2 (the host runs two steps ahead of the records it reads)" if pipelined else
                                           "none (one set of slots; every step prepares, tracks and reads back before the next one starts)"),
                            "parallelism": f"pair list sharded by connected components (sequence segments) x{world}; gather: {gather_desc}",
                            "l2": "inputs (%.0f MB per step per GPU) exceed the 126 MB L2; no flush" % (h2d_bytes / 1e6) if h2d_bytes > 126e6 else
