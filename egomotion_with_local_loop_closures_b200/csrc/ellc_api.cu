@@ -104,6 +104,7 @@ struct ellc_handle {
     // per-batch staging / result buffers: ring of 4 by sequence number (two batches may be in flight, a third being staged, and the
     // records of a finished one still being downloaded); entry r is reused by batch seq+4 after batch seq has completed
     ellc_pair* d_pairs4[4]; ellc_result* d_results4[4]; int* d_order4[4]; int* d_gidx4[4]; int ring_cap[4]; long long res_seq[4];
+    bool res_taken[4];                                 // the records of the entry's last batch have been copied out (the entry may be regrown)
     ellc_pair* d_pairs; ellc_result* d_results; int* d_order;       // entry of the batch being launched / launched last
     ellc_result* d_eval_result;                        // ellc_gn_evaluate's own record (never clobbers an undownloaded batch)
     ellc_exchange* xc;                                 // multi-GPU result exchange (ellc_exchange_create), or null
@@ -386,16 +387,29 @@ static int after_upload(ellc_handle* h) {
 // Ring entry r = seq & 3 of the per-batch buffers; the caller has already waited for batch seq - 4, the previous user of the entry.
 // Growing it frees that batch's records: a pointer returned by ellc_track_batch_async is valid until three more batches have
 // been launched (include/ellc_gn.h).
+static int grow_ring_entry(ellc_handle* h, int r, int cap) {
+    cudaFree(h->d_pairs4[r]); cudaFree(h->d_results4[r]); cudaFree(h->d_order4[r]); cudaFree(h->d_gidx4[r]);
+    h->d_pairs4[r] = nullptr; h->d_results4[r] = nullptr; h->d_order4[r] = nullptr; h->d_gidx4[r] = nullptr; h->ring_cap[r] = 0;
+    CU_TRY(h, cudaMalloc(&h->d_pairs4[r], (size_t)cap * sizeof(ellc_pair)));
+    CU_TRY(h, cudaMalloc(&h->d_results4[r], (size_t)cap * sizeof(ellc_result)));
+    CU_TRY(h, cudaMalloc(&h->d_order4[r], (size_t)cap * sizeof(int)));
+    CU_TRY(h, cudaMalloc(&h->d_gidx4[r], (size_t)cap * sizeof(int)));
+    h->ring_cap[r] = cap;
+    return ELLC_OK;
+}
+// (Re)allocation of a ring entry is a cudaFree + cudaMalloc, i.e. an implicit device synchronisation plus milliseconds of driver time.
+// It must not trickle in one entry per batch (measured: the FOURTH batch of a new size, the first to reuse entry 0, stalled the
+// caller's pipelined loop for 1 - 185 ms): when one entry has to grow, every other entry that is idle -- never used, or its last
+// batch complete and its records copied out -- grows with it.
 static int ensure_ring_cap(ellc_handle* h, int r, int n, bool want_trace) {
     if (n > h->ring_cap[r]) {
-        cudaFree(h->d_pairs4[r]); cudaFree(h->d_results4[r]); cudaFree(h->d_order4[r]); cudaFree(h->d_gidx4[r]);
-        h->d_pairs4[r] = nullptr; h->d_results4[r] = nullptr; h->d_order4[r] = nullptr; h->d_gidx4[r] = nullptr; h->ring_cap[r] = 0;
-        int cap = n < 256 ? 256 : n;
-        CU_TRY(h, cudaMalloc(&h->d_pairs4[r], (size_t)cap * sizeof(ellc_pair)));
-        CU_TRY(h, cudaMalloc(&h->d_results4[r], (size_t)cap * sizeof(ellc_result)));
-        CU_TRY(h, cudaMalloc(&h->d_order4[r], (size_t)cap * sizeof(int)));
-        CU_TRY(h, cudaMalloc(&h->d_gidx4[r], (size_t)cap * sizeof(int)));
-        h->ring_cap[r] = cap;
+        const int cap = n < 256 ? 256 : n;
+        int rc = grow_ring_entry(h, r, cap);
+        if (rc) return rc;
+        for (int q = 0; q < 4; ++q) {
+            const bool idle = h->res_seq[q] == 0 || (h->res_seq[q] <= h->batch_done_seq && h->res_taken[q]);
+            if (q != r && h->ring_cap[q] < cap && idle) { rc = grow_ring_entry(h, q, cap); if (rc) return rc; }
+        }
     }
     if (want_trace) {
         const int64_t need = (int64_t)n * kLevels * ELLC_MAX_TRACE_ITERS;
@@ -690,6 +704,7 @@ static int track_launch(ellc_handle* h, int n, const ellc_pair* pairs, bool want
     CU_TRY(h, cudaEventRecord(h->batch_ev[r], ts));
     h->batch_seq = seq;
     h->res_seq[r] = seq;
+    h->res_taken[r] = xl != nullptr;                       // exchanged batches are read from the exchange tables, not from this buffer
     if (dev) {
         for (int v : *dev->frame_slots) h->fr_reader[v] = seq;
         for (int v : *dev->kf_slots) h->kf_reader[v] = seq;
@@ -1059,6 +1074,7 @@ int ellc_results_download(ellc_handle* h, const ellc_result* device_results, int
     CU_TRY(h, cudaMemcpyAsync(results, device_results, (size_t)n * sizeof(ellc_result), cudaMemcpyDeviceToHost, h->d2h_stream));
     CU_TRY(h, cudaStreamSynchronize(h->d2h_stream));
     note_done(h, seq);
+    h->res_taken[which] = true;
     return ELLC_OK;
 }
 
@@ -1074,6 +1090,7 @@ int ellc_track_batch(ellc_handle* h, int32_t n, const ellc_pair* pairs, ellc_res
                                          cudaMemcpyDeviceToHost, ts));
     CU_TRY(h, cudaStreamSynchronize(ts));
     note_done(h, h->batch_seq);
+    h->res_taken[h->batch_seq & 3] = true;
     return ELLC_OK;
 }
 
