@@ -18,14 +18,22 @@ def _stale():
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
+def _code_only(text):
+    """C / CUDA source without comments and with runs of whitespace collapsed (string literals are left alone)."""
+    import re
+    pat = re.compile(r'//[^\n]*|/\*.*?\*/|"(?:\\.|[^"\\])*"|\'(?:\\.|[^\'\\])*\'', re.S)
+    text = pat.sub(lambda m: m.group(0) if m.group(0)[0] in "\"'" else " ", text)
+    return re.sub(r"\s+", " ", text).strip()
+
+
 def source_hash():
-    """SHA-1 over the kernel / ABI sources: ellc_version() carries it, so that a profile (profiles/r02_traffic.json,
-    r02_sass_histogram.json) can be matched to the build it was taken from."""
+    """SHA-1 over the CODE of the kernel / ABI sources (comments and layout do not count): ellc_version() carries it, so that a
+    profile (profiles/r02_traffic.json, r02_sass_histogram.json) can be matched to the build it was taken from."""
     import hashlib
     h = hashlib.sha1()
     for f in sorted(SOURCES + HEADERS):
-        with open(os.path.join(CSRC, f), "rb") as fh:
-            h.update(f.encode() + b"\0" + fh.read())
+        with open(os.path.join(CSRC, f), "r", encoding="utf-8", errors="replace") as fh:
+            h.update(f.encode() + b"\0" + _code_only(fh.read()).encode())
     return h.hexdigest()[:12]
 
 
