@@ -527,7 +527,10 @@ def main():
     PIPE_DEPTH = int(os.environ.get("ELLC_PIPE_DEPTH", "2"))
     pipe = {"k": 0, "pending": [], "last": None, "launched": 0}
 
-    overlap = os.environ.get("ELLC_OVERLAP") == "1"           # experiment: consecutive batches not serialised (measured slower)
+    # Consecutive forward batches run on the library's two tracking streams and overlap at their tails (the head of batch k+1 and its
+    # preparation fill the last wave of batch k): 345.9k against 342.7k tracks/s serialised (ELLC_OVERLAP=0; tools, profiles/r02_variants.md).
+    # Loop-closure batches share the keyframes' weight images and are serialised by the library.
+    overlap = os.environ.get("ELLC_OVERLAP", "1") == "1" and not lc
 
     def note_kernel_time():
         # CUDA events around the tracking kernel of the batch just fetched, on its own stream.  (With ELLC_OVERLAP=1 the kernels of

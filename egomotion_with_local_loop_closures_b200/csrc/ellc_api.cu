@@ -71,7 +71,7 @@ struct ellc_handle {
                                                        // synchronous main-stream calls (evaluate, read-backs) be ordered explicitly
     cudaEvent_t main_ev;                               // recorded on the main stream at every batch launch; the batch's stream waits for it
     cudaEvent_t hyp_ev; bool hyp_pending;              // depth pyramids built from hypotheses on the main stream (prep stream must wait)
-    bool overlap_batches;                              // ELLC_OVERLAP=0 serialises consecutive batches (A/B measurement)
+    bool overlap_batches;                              // consecutive forward batches overlap at their tails (default; ELLC_OVERLAP=0 serialises them: A/B measurement)
     cudaStream_t copy_stream;                          // H2D uploads of images / depth / variance (overlap with compute)
     cudaStream_t d2h_stream;                           // result downloads of finished batches
     cudaEvent_t ev0r[4], ev1r[4];                      // track-kernel timing events of the last four batches (index: sequence & 3)
@@ -269,7 +269,7 @@ int ellc_create(const ellc_config* cfg, ellc_handle** out) {
     // MEASURED (round 2, 4608 pairs per batch): letting batch k+1 start while batch k still runs does NOT just fill its last wave --
     // its CTAs are dispatched as soon as its preparation is done, the two batches then share the SMs for most of their run time
     // with two different working sets in L2: 270k tracks/s against 335k with the batches serialised.  Off unless ELLC_OVERLAP=1.
-    h->overlap_batches = false;
+    h->overlap_batches = true;
     if (const char* e = std::getenv("ELLC_OVERLAP")) h->overlap_batches = (*e == '1');
     CR_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     CR_TRY(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
