@@ -142,6 +142,23 @@ def setup_bytes(n_frames, n_kf):
     return n_frames * pyr + n_kf * (pyr + 5.0 * P.sum())
 
 
+def input_bytes_per_step(n_frames, n_kf, n_pairs):
+    """Host inputs of one step on one GPU: u8 level-0 images of the frames and keyframes, f32 depth and variance pyramids of the
+    keyframes (cv::pyrDown level sizes), the pair list."""
+    dims = [(W >> l, H >> l) for l in range(4)]                # depth / variance arrays: ORIG_COLS >> L x ORIG_ROWS >> L
+    return n_frames * W * H + n_kf * (W * H + 2 * 4 * sum(w * h for w, h in dims)) + n_pairs * 36
+
+
+def workload_config(conf, n_kf, n_frames, pairs_per_frame, n_pairs, lc=False):
+    """`config` of the bench line: the WORKLOAD and nothing else -- identical in our arm and in the reference arm (which tracks a
+    bounded sample of the same pair list; how each arm runs it is under `implementation`)."""
+    inb = input_bytes_per_step(n_frames, n_kf, n_pairs)
+    return {"workload": conf["workload"] + ("_lc_const_weight" if lc else ""), "width": W, "height": H, "keyframes_per_gpu": n_kf,
+            "frames_per_gpu": n_frames, "pairs_per_gpu_per_step": n_pairs, "pairs_per_frame": pairs_per_frame,
+            "l2": ("inputs (%.0f MB per step per GPU) exceed the 126 MB L2; no flush" % (inb / 1e6)) if inb > 126e6 else
+                  ("inputs (%.1f MB) fit the L2: this configuration measures latency of a resident working set, not bandwidth" % (inb / 1e6))}
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # clocks
 # ----------------------------------------------------------------------------------------------------------------
@@ -282,11 +299,11 @@ def run_reference(args, rank, world, conf):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": conf["workload"], "width": W, "height": H, "keyframes_per_gpu": args.keyframes,
-                       "frames_per_gpu": args.frames, "pairs_per_frame": args.pairs_per_frame, "pairs_per_step": n_pairs,
-                       "note": "CPU oracle restatement of the reference tracker (g++ -std=c++11 -O3), bit-identical to the reference's own code where "
-                               "that could be compiled (DESIGN.md section 2); it omits the reference's per-pixel cv::Mat/cv::String overhead, so it is "
-                               "FASTER than the real binary; a bounded sample of the same pair list as our arm (a rate: tracks/s)"},
+            "config": workload_config(conf, args.keyframes, args.frames, args.pairs_per_frame, len(wl["kf_idx"])),
+            "implementation": {"sample_pairs_per_step": n_pairs,
+                               "note": "CPU oracle restatement of the reference tracker (g++ -std=c++11 -O3), bit-identical to the reference's own code where "
+                                       "that could be compiled (DESIGN.md section 2); it omits the reference's per-pixel cv::Mat/cv::String overhead, so it is "
+                                       "FASTER than the real binary; each step tracks a bounded sample -- the first pairs -- of the workload's pair list (a rate: tracks/s)"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                              "reference_faithful": faithful},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -768,16 +785,14 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": conf["workload"] + ("_lc_const_weight" if lc else ""), "width": W, "height": H, "keyframes_per_gpu": args.keyframes,
-                           "frames_per_gpu": args.frames, "pairs_per_gpu_per_step": n_pairs, "pairs_per_frame": args.pairs_per_frame,
-                           "arithmetic": args.arith, "ctas_per_pair": args.cluster or "auto", "pairs_per_cta": args.pairs_per_cta or "auto", "library": lib_version,
-                           "pipelining": ("resident inputs held twice; steps alternate between the two sets of slots: preparation of step k+1 on a "
-                                          "low-priority stream overlaps the tracking kernel of step k, records of step k fetched during step k+2 (the host runs two steps ahead of the records it reads)" if pipelined else
-                                          "none (one set of slots; every step prepares, tracks and reads back before the next one starts)"),
-                           "parallelism": f"pair list sharded by connected components (sequence segments) x{world}; gather: {gather_desc}",
-                           "l2": "inputs (%.0f MB per step per GPU) exceed the 126 MB L2; no flush" % (h2d_bytes / 1e6) if h2d_bytes > 126e6 else
-                                 "inputs (%.1f MB) fit the L2: this configuration measures latency of a resident working set, not bandwidth" % (h2d_bytes / 1e6),
-                           "setup_bytes_per_step": setup_bytes(args.frames, args.keyframes) * world, "setup_seconds": setup_s},
+                "config": workload_config(conf, args.keyframes, args.frames, args.pairs_per_frame, n_pairs, lc),
+                "implementation": {
+                    "arithmetic": args.arith, "ctas_per_pair": args.cluster or "auto", "pairs_per_cta": args.pairs_per_cta or "auto", "library": lib_version,
+                    "pipelining": ("resident inputs held twice; steps alternate between the two sets of slots: preparation of step k+1 on a "
+                                   "low-priority stream overlaps the tracking kernel of step k, records of step k fetched during step k+2 (the host runs two steps ahead of the records it reads)" if pipelined else
+                                   "none (one set of slots; every step prepares, tracks and reads back before the next one starts)"),
+                    "parallelism": f"pair list sharded by connected components (sequence segments) x{world}; gather: {gather_desc}",
+                    "setup_bytes_per_step": setup_bytes(args.frames, args.keyframes) * world, "setup_seconds": setup_s},
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
         if n_pairs == 1:
             line["latency_ms_per_track"] = ms / args.steps
