@@ -241,7 +241,9 @@ int ellc_prepare_async(ellc_handle* h, int32_t n_frames, const int32_t* frame_sl
 int ellc_track_batch(ellc_handle* h, int32_t n, const ellc_pair* pairs, ellc_result* results, ellc_iter_trace* trace);
 
 /* Same, asynchronous: only enqueues.  Results stay on the device in a ring of four buffers: the returned pointer
- * stays valid until three more track calls have been made on this handle.  Uploads run on their own copy stream, so the uploads of
+ * stays valid until three more track calls have been made on this handle (the buffers grow when a larger batch arrives -- all idle
+ * ones together, once per batch size; a buffer whose records have not been fetched yet is left alone).  Consecutive forward batches
+ * run on two internal streams and overlap at their tails.  Uploads run on their own copy stream, so the uploads of
  * the next batch overlap this batch's kernels as long as they go to slots this batch does not read (slot reuse is
  * detected and ordered automatically). */
 int ellc_track_batch_async(ellc_handle* h, int32_t n, const ellc_pair* pairs, const ellc_result** device_results);
